@@ -1,0 +1,130 @@
+/* tfft.h -- C ABI of the B200-native TurtleFFT spectral hot path.
+ *
+ * The reference (rickenator/steganosaurus) has no plugin/FFI interface: its hot path is a set
+ * of `static` functions in steganosaurus/src/steganosaur.cpp (cited below as S:line) called from
+ * do_embed (S:907-1109) and do_extract (S:1112-1312).  This header is the seam a maintainer
+ * would bind instead of those calls: the host keeps PNG I/O, KDF, AEAD,
+ * framing and the turtlewalk, emits a bin-index array and a bit array, and hands them over.
+ *
+ * Conventions
+ *   images   uint8 [n][H][W][3] interleaved RGB, exactly what stbi_load(...,3) returns (S:909)
+ *   bins     uint32, one per embedded/read bit: plane<<30 | (y*PW + x) with PW = next_pow2(W),
+ *            PH = next_pow2(H) (S:393-394); ONE bin list is shared by the whole batch (the
+ *            walk is cover-independent, S:797-799)
+ *   bits     uint8 0/1, one per byte (S:455-459), [n][nbits] -- every image has its own bits
+ *   spectra  complex<double> as (re,im) pairs, [3][PH][PW] row-major, reference sign
+ *            convention: forward = sum x[n] e^{+2*pi*i*nk/N} (S:347)
+ *   errors   integer codes, never exit(); tfft_strerror() names them
+ *   threads  a tfft_ctx is NOT thread-safe: one ctx per GPU per host thread
+ *   memory   the caller owns every buffer passed in; the library owns its device workspace
+ *
+ * Entry points ending in _dev take DEVICE pointers and a cudaStream_t (as void*), enqueue
+ * their work on that stream and return without synchronising.  The others take HOST
+ * pointers (pinned memory from tfft_host_alloc recommended), copy in/out on internal
+ * streams and are synchronous at return.
+ */
+#ifndef TFFT_H
+#define TFFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFFT_ABI_VERSION 1
+
+enum {
+    TFFT_OK = 0,
+    TFFT_E_INVALID = 1,     /* bad argument (null pointer, non-positive size, rep not in 1,3,7 ...) */
+    TFFT_E_CUDA = 2,        /* a CUDA call failed; tfft_last_cuda_error() has the text */
+    TFFT_E_CAPACITY = 3,    /* nbits > usable for at least one image (S:1009-1012) */
+    TFFT_E_NOMEM = 4,       /* workspace does not fit the device */
+    TFFT_E_UNSUPPORTED = 5, /* padded dimension outside [TFFT_MIN_DIM, TFFT_MAX_DIM] */
+    TFFT_E_STATE = 6        /* tfft_read_bits without resident spectra */
+};
+
+#define TFFT_MIN_DIM 16
+#define TFFT_MAX_DIM 16384
+
+typedef struct tfft_ctx tfft_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+/* Create a context on CUDA device `device`; owns streams, twiddle tables, workspaces. */
+int tfft_create(int device, tfft_ctx** out);
+void tfft_destroy(tfft_ctx* ctx);
+int tfft_abi_version(void);
+const char* tfft_strerror(int code);
+const char* tfft_last_cuda_error(const tfft_ctx* ctx);
+/* Upper bound for the spectrum workspace in bytes (default: 40% of device memory). */
+int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes);
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+void* tfft_host_alloc(size_t bytes);
+void tfft_host_free(void* p);
+/* Number of kernels this library has launched through ctx since creation. */
+uint64_t tfft_launch_count(const tfft_ctx* ctx);
+
+/* ---- embed: replaces S:912-923, S:997-1012, S:1015, S:1086, S:1100-1103 ------------------
+ * For each image: plane split (to_planes_u8 S:383), optional (-1)^(x+y) (apply_center S:392),
+ * implicit zero pad to PHxPW (pad_to_fft S:393), forward 2-D FFT (fft2d S:359), median |F| per
+ * plane (median_abs S:404), capacity count (S:999-1007), phase write at the bins
+ * (write_bit_on_bin S:712: |F| kept, phase = +-alpha (+ jitter[i]), conjugate bin mirrored),
+ * inverse 2-D FFT, crop (ifft_crop S:399), centre, round/clamp/interleave (from_planes_u8 S:387).
+ *   jitter  NULL or [nbits] radians added to the target phase (KS::jitter, S:690)
+ *   usable  NULL or [n]     capacity in bits as the reference counts it
+ *   median  NULL or [n][3]  median |F| per plane
+ * Images with nbits > usable are passed through unmodified (their spectrum is not touched)
+ * and the call returns TFFT_E_CAPACITY after finishing the rest of the batch. */
+int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                     const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
+                     double alpha, int center, double magmin, double rmin, double rmax,
+                     uint8_t* stego, uint64_t* usable, double* median);
+int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, int H,
+                         const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits,
+                         const double* d_jitter, double alpha, int center, double magmin,
+                         double rmin, double rmax, uint8_t* d_stego, uint64_t* d_usable,
+                         double* d_median, void* stream);
+
+/* ---- extract: replaces S:1116-1123, S:1209, S:1228, S:1266-1268 --------------------------
+ * Forward 2-D FFT of every image, phase read at the bins (read_bit_from_bin S:734, ties -> 1),
+ * majority vote over `rep` consecutive bins (rep3/rep7_decode_bits S:468/S:501; rep=1: none)
+ * and MSB-first packing (bytes_from_bits S:447).
+ *   out_bytes  [n][ceil(floor(nbins/rep)/8)] decoded bytes (may be NULL)
+ *   raw_bits   [n][nbins] pre-vote bits (may be NULL) */
+int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
+                      const uint32_t* bins, size_t nbins, int rep, const double* jitter,
+                      double alpha, int center, uint8_t* out_bytes, uint8_t* raw_bits);
+int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
+                          const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter,
+                          double alpha, int center, uint8_t* d_out_bytes, uint8_t* d_raw_bits,
+                          void* stream);
+
+/* Two-phase extract for the data dependency at S:1253 (payload length is only known after the
+ * header has been decoded): tfft_forward_batch keeps the spectra of the batch resident in the
+ * context; tfft_read_bits may then be called any number of times (header: 912 bins rep 3,
+ * payload: 56*(clen+16) bins rep 7).  The batch must fit the workspace (TFFT_E_NOMEM if not). */
+int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center);
+int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep,
+                   const double* jitter, double alpha, uint8_t* out_bytes, uint8_t* raw_bits);
+
+/* ---- parity / measurement hooks ----------------------------------------------------------
+ * Forward spectra (S:359-366 after S:383-398) of one image: out_c64 = [3][PH][PW] (re,im). */
+int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int center,
+                          double* out_c64);
+/* Plain batched complex 2-D FFT, in place, reference sign/scale conventions (fft2d S:359). */
+int tfft_fft2d(tfft_ctx* ctx, double* data_c64, int n, int PH, int PW, int inverse);
+int tfft_fft2d_dev(tfft_ctx* ctx, double* d_data_c64, int n, int PH, int PW, int inverse, void* stream);
+/* One 1-D pass only, on a device array of n planes [PH][PW]: axis 0 = along rows (x),
+ * axis 1 = along columns (y).  Used by bench.py to time a single pass for the roofline. */
+int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data_c64, int n, int PH, int PW, int axis,
+                      int inverse, void* stream);
+/* median |F| and capacity count of device spectra [n][3][PH][PW] (S:404-409, S:999-1007). */
+int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec_c64, int n, int PH, int PW,
+                             double magmin, double rmin, double rmax, double* d_median,
+                             uint64_t* d_usable, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFFT_H */

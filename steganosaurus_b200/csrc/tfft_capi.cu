@@ -1,0 +1,593 @@
+// tfft_capi.cu -- the C ABI declared in include/tfft.h: context, workspaces, chunked
+// double-buffered host<->device pipeline, and the kernel sequences for embed / extract.
+// Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
+#include "../../include/tfft.h"
+#include "tfft_kernels.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+using namespace tfft;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf spec, in, out, bits, med, medians, usable, outbytes, raw;
+    uint64_t* h_usable = nullptr;  // pinned staging for the capacity verdict
+    size_t h_usable_cap = 0;
+};
+
+}  // namespace
+
+struct tfft_ctx {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    size_t total_mem = 0;
+    size_t ws_limit = 0;
+    double2* d_tw = nullptr;
+    Slot slot[2];
+    DevBuf bins, jitter;
+    uint64_t launches = 0;
+    int fft_impl = 1;
+    // resident spectra for the two-phase extract
+    int res_n = 0, res_PH = 0, res_PW = 0;
+    char cuda_err[256] = {0};
+};
+
+namespace {
+
+constexpr uint32_t CAND_CAP = 1u << 16;
+constexpr int MAX_CHUNK = 64;
+
+int fail_cuda(tfft_ctx* c, cudaError_t e, const char* where) {
+    snprintf(c->cuda_err, sizeof(c->cuda_err), "%.160s: %.80s", where, cudaGetErrorString(e));
+    return TFFT_E_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);   \
+    } while (0)
+
+int ensure(tfft_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return TFFT_OK;
+    if (b.p) { CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return TFFT_E_NOMEM; }
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaMalloc");
+    b.cap = bytes;
+    return TFFT_OK;
+}
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+inline int next_pow2_i(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+inline int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+struct Geom {
+    int W, H, PW, PH, lw, lh;
+    size_t P;          // PH*PW
+    size_t img_bytes;  // H*W*3
+};
+int make_geom(int W, int H, Geom& g) {
+    if (W <= 0 || H <= 0) return TFFT_E_INVALID;
+    g.W = W; g.H = H;
+    g.PW = next_pow2_i(W); g.PH = next_pow2_i(H);  // S:394
+    // the FFT passes need at least 2 points per axis; tiny images are padded further only by
+    // the reference's own rule, so anything below TFFT_MIN_DIM is refused rather than changed.
+    if (g.PW > TFFT_MAX_DIM || g.PH > TFFT_MAX_DIM) return TFFT_E_UNSUPPORTED;
+    if (g.PW < TFFT_MIN_DIM || g.PH < TFFT_MIN_DIM) return TFFT_E_UNSUPPORTED;
+    g.lw = ilog2(g.PW); g.lh = ilog2(g.PH);
+    g.P = (size_t)g.PW * g.PH;
+    g.img_bytes = (size_t)W * H * 3;
+    return TFFT_OK;
+}
+
+Launcher make_launcher(tfft_ctx* ctx, cudaStream_t s) {
+    Launcher L;
+    L.stream = s;
+    L.launch_counter = &ctx->launches;
+    L.sm_count = ctx->sm_count;
+    L.smem_optin = ctx->smem_optin;
+    L.fft_impl = ctx->fft_impl;
+    return L;
+}
+
+// images per chunk so that `nslots` spectrum workspaces fit the limit
+int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
+    const size_t per_img = 3 * g.P * sizeof(double2);
+    size_t c = ctx->ws_limit / nslots / per_img;
+    if (c < 1) c = 1;
+    if (c > (size_t)MAX_CHUNK) c = MAX_CHUNK;
+    if (c > (size_t)n) c = n;
+    return (int)c;
+}
+
+int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, size_t nbits, size_t outbytes, size_t rawbytes) {
+    int rc;
+    const int nplanes = chunk * 3;
+    if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.P * sizeof(double2)))) return rc;
+    if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, CAND_CAP)))) return rc;
+    if ((rc = ensure(ctx, S.medians, sizeof(double) * nplanes))) return rc;
+    if ((rc = ensure(ctx, S.usable, sizeof(uint64_t) * chunk))) return rc;
+    if (need_io) {
+        if ((rc = ensure(ctx, S.in, (size_t)chunk * g.img_bytes))) return rc;
+        if ((rc = ensure(ctx, S.out, (size_t)chunk * g.img_bytes))) return rc;
+        if (nbits && (rc = ensure(ctx, S.bits, (size_t)chunk * nbits))) return rc;
+    }
+    if (outbytes && (rc = ensure(ctx, S.outbytes, (size_t)chunk * outbytes))) return rc;
+    if (rawbytes && (rc = ensure(ctx, S.raw, (size_t)chunk * rawbytes))) return rc;
+    if (S.h_usable_cap < (size_t)chunk) {
+        if (S.h_usable) cudaFreeHost(S.h_usable);
+        CK(cudaHostAlloc((void**)&S.h_usable, sizeof(uint64_t) * MAX_CHUNK, cudaHostAllocDefault));
+        S.h_usable_cap = MAX_CHUNK;
+    }
+    return TFFT_OK;
+}
+
+// ---- kernel sequences -----------------------------------------------------------------------
+PassArgs base_args(tfft_ctx* ctx, double2* spec, int nimg, const Geom& g, int center) {
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.spec = spec;
+    a.tw = ctx->d_tw;
+    a.nplanes = nimg * 3;
+    a.W = g.W; a.H = g.H; a.PW = g.PW; a.PH = g.PH;
+    a.center = center;
+    a.in_rows = g.PH;
+    a.out_rows = g.PH;
+    return a;
+}
+
+// forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
+int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_t* d_img, int nimg, const Geom& g, int center) {
+    PassArgs a = base_args(ctx, spec, nimg, g, center);
+    a.img_in = d_img;
+    a.axis = 0; a.log2n = g.lw; a.inverse = 0;
+    a.in_rows = g.H;  // rows >= H are zero padding (S:395)
+    CK(launch_fft_pass(L, a));
+    a.img_in = nullptr;
+    a.in_rows = g.PH;
+    a.axis = 1; a.log2n = g.lh;
+    CK(launch_fft_pass(L, a));
+    return TFFT_OK;
+}
+
+// inverse 2-D FFT + crop + quantise (S:1100-1103): columns first so that the last pass runs
+// along image rows and can emit interleaved u8 directly.
+int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, uint8_t* d_img, int nimg, const Geom& g, int center) {
+    PassArgs a = base_args(ctx, spec, nimg, g, center);
+    a.axis = 1; a.log2n = g.lh; a.inverse = 1;
+    CK(launch_fft_pass(L, a));
+    a.axis = 0; a.log2n = g.lw;
+    a.img_out = d_img;
+    a.out_rows = g.H;  // rows >= H are cropped away (S:399-403)
+    CK(launch_fft_pass(L, a));
+    return TFFT_OK;
+}
+
+int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cover, int nimg, const Geom& g,
+                const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits, const double* d_jitter,
+                double alpha, int center, double magmin, double rmin, double rmax,
+                uint8_t* d_stego, uint64_t* d_usable, double* d_median) {
+    double2* spec = (double2*)S.spec.p;
+    int rc = forward_images(ctx, L, spec, d_cover, nimg, g, center);
+    if (rc) return rc;
+    MedianWork mw;
+    median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
+    const int m = std::min(g.PH, g.PW);
+    CK(launch_median_capacity(L, spec, nimg * 3, g.PH, g.PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
+    CK(launch_embed(L, spec, nimg, g.PH, g.PW, d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable));
+    return inverse_images(ctx, L, spec, d_stego, nimg, g, center);
+}
+
+int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_stego, int nimg, const Geom& g,
+                  const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter, double alpha, int center,
+                  uint8_t* d_out_bytes, uint8_t* d_raw) {
+    double2* spec = (double2*)S.spec.p;
+    int rc = forward_images(ctx, L, spec, d_stego, nimg, g, center);
+    if (rc) return rc;
+    CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw));
+    return TFFT_OK;
+}
+
+int upload_bins(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, const double* jitter, cudaStream_t s) {
+    int rc;
+    if (nbins == 0) return TFFT_OK;
+    if ((rc = ensure(ctx, ctx->bins, sizeof(uint32_t) * nbins))) return rc;
+    CK(cudaMemcpyAsync(ctx->bins.p, bins, sizeof(uint32_t) * nbins, cudaMemcpyHostToDevice, s));
+    if (jitter) {
+        if ((rc = ensure(ctx, ctx->jitter, sizeof(double) * nbins))) return rc;
+        CK(cudaMemcpyAsync(ctx->jitter.p, jitter, sizeof(double) * nbins, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));  // both slot streams read the shared bin list
+    return TFFT_OK;
+}
+
+inline size_t dec_bytes(size_t nbins, int rep) { return (nbins / (size_t)rep + 7) / 8; }
+
+// host-side sanity of a bin list: plane in 0..2 and linear index inside the padded plane
+bool bins_ok(const uint32_t* bins, size_t n, size_t P) {
+    for (size_t i = 0; i < n; i++)
+        if ((bins[i] >> 30) > 2 || (size_t)(bins[i] & 0x3FFFFFFFu) >= P) return false;
+    return true;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int tfft_abi_version(void) { return TFFT_ABI_VERSION; }
+
+const char* tfft_strerror(int code) {
+    switch (code) {
+        case TFFT_OK: return "ok";
+        case TFFT_E_INVALID: return "invalid argument";
+        case TFFT_E_CUDA: return "CUDA error";
+        case TFFT_E_CAPACITY: return "message too large for the cover's capacity";
+        case TFFT_E_NOMEM: return "device workspace does not fit";
+        case TFFT_E_UNSUPPORTED: return "padded image dimension not supported";
+        case TFFT_E_STATE: return "no resident spectra (call tfft_forward_batch first)";
+        default: return "unknown error";
+    }
+}
+
+const char* tfft_last_cuda_error(const tfft_ctx* ctx) { return ctx ? ctx->cuda_err : ""; }
+uint64_t tfft_launch_count(const tfft_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* tfft_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void tfft_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int tfft_create(int device, tfft_ctx** out) {
+    if (!out) return TFFT_E_INVALID;
+    *out = nullptr;
+    tfft_ctx* ctx = new tfft_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete ctx; cudaGetLastError(); return TFFT_E_CUDA; }
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device); ctx->sm_count = v;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device); ctx->smem_optin = (size_t)v;
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    ctx->total_mem = tot;
+    ctx->ws_limit = (size_t)((double)tot * 0.40);
+    const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
+    ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : 1;
+    for (int i = 0; i < 2; i++)
+        if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
+    if (e == cudaSuccess) e = build_twiddles(ctx->d_tw, ctx->slot[0].stream);
+    if (e != cudaSuccess) { tfft_destroy(ctx); cudaGetLastError(); return TFFT_E_CUDA; }
+    *out = ctx;
+    return TFFT_OK;
+}
+
+void tfft_destroy(tfft_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        Slot& S = ctx->slot[i];
+        release(S.spec); release(S.in); release(S.out); release(S.bits); release(S.med);
+        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw);
+        if (S.h_usable) cudaFreeHost(S.h_usable);
+        if (S.stream) cudaStreamDestroy(S.stream);
+    }
+    release(ctx->bins); release(ctx->jitter);
+    if (ctx->d_tw) cudaFree(ctx->d_tw);
+    delete ctx;
+}
+
+int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes) {
+    if (!ctx || bytes == 0) return TFFT_E_INVALID;
+    ctx->ws_limit = bytes;
+    return TFFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, int H,
+                         const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits,
+                         const double* d_jitter, double alpha, int center, double magmin,
+                         double rmin, double rmax, uint8_t* d_stego, uint64_t* d_usable,
+                         double* d_median, void* stream) {
+    if (!ctx || !d_cover || !d_stego || n < 0 || (nbits && (!d_bins || !d_bits))) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(W, H, g);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    const int chunk = chunk_for(ctx, g, n, 1);
+    Slot& S = ctx->slot[0];
+    if ((rc = ensure_slot(ctx, S, g, chunk, false, 0, 0, 0))) return rc;
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = std::min(chunk, n - i0);
+        uint64_t* us = d_usable ? d_usable + i0 : (uint64_t*)S.usable.p;
+        double* med = d_median ? d_median + (size_t)i0 * 3 : (double*)S.medians.p;
+        rc = embed_chunk(ctx, L, S, d_cover + (size_t)i0 * g.img_bytes, m, g, d_bins, d_bits + (size_t)i0 * nbits, nbits,
+                         d_jitter, alpha, center, magmin, rmin, rmax, d_stego + (size_t)i0 * g.img_bytes, us, med);
+        if (rc) return rc;
+    }
+    return TFFT_OK;
+}
+
+int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                     const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
+                     double alpha, int center, double magmin, double rmin, double rmax,
+                     uint8_t* stego, uint64_t* usable, double* median) {
+    if (!ctx || !cover || !stego || n < 0 || (nbits && (!bins || !bits))) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(W, H, g);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    const int chunk = chunk_for(ctx, g, n, 2);
+    const int nslots = (n > chunk) ? 2 : 1;
+    for (int s = 0; s < nslots; s++)
+        if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
+    if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
+    bool over = false;
+    int ci = 0;
+    std::vector<int> pending_i0[2], pending_m[2];
+    for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
+        Slot& S = ctx->slot[ci & 1];
+        const int m = std::min(chunk, n - i0);
+        cudaStream_t st = S.stream;
+        // the pinned verdict buffer of this slot is about to be overwritten: drain it first
+        if (!pending_i0[ci & 1].empty()) {
+            CK(cudaStreamSynchronize(st));
+            const int p0 = pending_i0[ci & 1].back(), pm = pending_m[ci & 1].back();
+            for (int k = 0; k < pm; k++) {
+                if (usable) usable[p0 + k] = S.h_usable[k];
+                if (S.h_usable[k] < (uint64_t)nbits) over = true;
+            }
+            pending_i0[ci & 1].clear(); pending_m[ci & 1].clear();
+        }
+        CK(cudaMemcpyAsync(S.in.p, cover + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
+        if (nbits) CK(cudaMemcpyAsync(S.bits.p, bits + (size_t)i0 * nbits, (size_t)m * nbits, cudaMemcpyHostToDevice, st));
+        Launcher L = make_launcher(ctx, st);
+        rc = embed_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, (const uint8_t*)S.bits.p, nbits,
+                         jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, magmin, rmin, rmax,
+                         (uint8_t*)S.out.p, (uint64_t*)S.usable.p, (double*)S.medians.p);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(stego + (size_t)i0 * g.img_bytes, S.out.p, (size_t)m * g.img_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(S.h_usable, S.usable.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
+        if (median) CK(cudaMemcpyAsync(median + (size_t)i0 * 3, S.medians.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+        pending_i0[ci & 1].push_back(i0); pending_m[ci & 1].push_back(m);
+    }
+    for (int s = 0; s < 2; s++) {
+        if (pending_i0[s].empty()) continue;
+        Slot& S = ctx->slot[s];
+        CK(cudaStreamSynchronize(S.stream));
+        const int p0 = pending_i0[s].back(), pm = pending_m[s].back();
+        for (int k = 0; k < pm; k++) {
+            if (usable) usable[p0 + k] = S.h_usable[k];
+            if (S.h_usable[k] < (uint64_t)nbits) over = true;
+        }
+    }
+    return over ? TFFT_E_CAPACITY : TFFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
+                          const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter,
+                          double alpha, int center, uint8_t* d_out_bytes, uint8_t* d_raw_bits, void* stream) {
+    if (!ctx || !d_stego || n < 0 || (nbins && !d_bins) || !(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(W, H, g);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    const int chunk = chunk_for(ctx, g, n, 1);
+    Slot& S = ctx->slot[0];
+    if ((rc = ensure_slot(ctx, S, g, chunk, false, 0, 0, 0))) return rc;
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    const size_t nb = dec_bytes(nbins, rep);
+    for (int i0 = 0; i0 < n; i0 += chunk) {
+        const int m = std::min(chunk, n - i0);
+        rc = extract_chunk(ctx, L, S, d_stego + (size_t)i0 * g.img_bytes, m, g, d_bins, nbins, rep, d_jitter, alpha, center,
+                           d_out_bytes ? d_out_bytes + (size_t)i0 * nb : nullptr,
+                           d_raw_bits ? d_raw_bits + (size_t)i0 * nbins : nullptr);
+        if (rc) return rc;
+    }
+    return TFFT_OK;
+}
+
+int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
+                      const uint32_t* bins, size_t nbins, int rep, const double* jitter,
+                      double alpha, int center, uint8_t* out_bytes, uint8_t* raw_bits) {
+    if (!ctx || !stego || n < 0 || (nbins && !bins) || !(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(W, H, g);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    const int chunk = chunk_for(ctx, g, n, 2);
+    const int nslots = (n > chunk) ? 2 : 1;
+    const size_t nb = dec_bytes(nbins, rep);
+    for (int s = 0; s < nslots; s++)
+        if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, 0, out_bytes ? nb : 0, raw_bits ? nbins : 0))) return rc;
+    if ((rc = upload_bins(ctx, bins, nbins, jitter, ctx->slot[0].stream))) return rc;
+    int ci = 0;
+    for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
+        Slot& S = ctx->slot[ci & 1];
+        const int m = std::min(chunk, n - i0);
+        cudaStream_t st = S.stream;
+        CK(cudaMemcpyAsync(S.in.p, stego + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
+        Launcher L = make_launcher(ctx, st);
+        rc = extract_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, nbins, rep,
+                           jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center,
+                           out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr);
+        if (rc) return rc;
+        if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes + (size_t)i0 * nb, S.outbytes.p, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
+        if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits + (size_t)i0 * nbins, S.raw.p, (size_t)m * nbins, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < nslots; s++) CK(cudaStreamSynchronize(ctx->slot[s].stream));
+    return TFFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center) {
+    if (!ctx || !img || n <= 0) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(W, H, g);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    if ((size_t)n * 3 * g.P * sizeof(double2) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
+    Slot& S = ctx->slot[0];
+    if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
+    CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
+    Launcher L = make_launcher(ctx, S.stream);
+    if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (const uint8_t*)S.in.p, n, g, center))) return rc;
+    CK(cudaStreamSynchronize(S.stream));
+    ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW;
+    return TFFT_OK;
+}
+
+int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, const double* jitter,
+                   double alpha, uint8_t* out_bytes, uint8_t* raw_bits) {
+    if (!ctx || (nbins && !bins) || !(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+    if (ctx->res_n <= 0) return TFFT_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    Slot& S = ctx->slot[0];
+    const int n = ctx->res_n;
+    const size_t P = (size_t)ctx->res_PH * ctx->res_PW;
+    if (!bins_ok(bins, nbins, P)) return TFFT_E_INVALID;
+    int rc;
+    const size_t nb = dec_bytes(nbins, rep);
+    if (out_bytes && nb && (rc = ensure(ctx, S.outbytes, (size_t)n * nb))) return rc;
+    if (raw_bits && nbins && (rc = ensure(ctx, S.raw, (size_t)n * nbins))) return rc;
+    if ((rc = upload_bins(ctx, bins, nbins, jitter, S.stream))) return rc;
+    Launcher L = make_launcher(ctx, S.stream);
+    CK(launch_extract(L, (const double2*)S.spec.p, n, ctx->res_PH, ctx->res_PW, (const uint32_t*)ctx->bins.p, nbins, rep,
+                      jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
+                      out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr));
+    if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes, S.outbytes.p, (size_t)n * nb, cudaMemcpyDeviceToHost, S.stream));
+    if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits, S.raw.p, (size_t)n * nbins, cudaMemcpyDeviceToHost, S.stream));
+    CK(cudaStreamSynchronize(S.stream));
+    return TFFT_OK;
+}
+
+int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int center, double* out_c64) {
+    if (!out_c64) return TFFT_E_INVALID;
+    int rc = tfft_forward_batch(ctx, img, 1, W, H, center);
+    if (rc) return rc;
+    Slot& S = ctx->slot[0];
+    CK(cudaMemcpy(out_c64, S.spec.p, 3 * (size_t)ctx->res_PH * ctx->res_PW * sizeof(double2), cudaMemcpyDeviceToHost));
+    return TFFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int fft2d_planes(tfft_ctx* ctx, const Launcher& L, double2* d, int nplanes, int PH, int PW, int inverse) {
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.spec = d; a.tw = ctx->d_tw; a.nplanes = nplanes;
+    a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
+    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
+    a.axis = 0; a.log2n = ilog2(PW);  // rows, then columns (S:361-365)
+    CK(launch_fft_pass(L, a));
+    a.axis = 1; a.log2n = ilog2(PH);
+    CK(launch_fft_pass(L, a));
+    return TFFT_OK;
+}
+static int check_dims(int PH, int PW) {
+    if (PH < 2 || PW < 2 || (PH & (PH - 1)) || (PW & (PW - 1))) return TFFT_E_INVALID;
+    if (PH > TFFT_MAX_DIM || PW > TFFT_MAX_DIM) return TFFT_E_UNSUPPORTED;
+    return TFFT_OK;
+}
+
+int tfft_fft2d_dev(tfft_ctx* ctx, double* d_data, int n, int PH, int PW, int inverse, void* stream) {
+    if (!ctx || !d_data || n < 0) return TFFT_E_INVALID;
+    int rc = check_dims(PH, PW);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    CK(cudaSetDevice(ctx->device));
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    return fft2d_planes(ctx, L, (double2*)d_data, n, PH, PW, inverse);
+}
+
+int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data, int n, int PH, int PW, int axis, int inverse, void* stream) {
+    if (!ctx || !d_data || n <= 0 || (axis != 0 && axis != 1)) return TFFT_E_INVALID;
+    int rc = check_dims(PH, PW);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.spec = (double2*)d_data; a.tw = ctx->d_tw; a.nplanes = n;
+    a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
+    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
+    a.axis = axis; a.log2n = ilog2(axis == 0 ? PW : PH);
+    CK(launch_fft_pass(L, a));
+    return TFFT_OK;
+}
+
+int tfft_fft2d(tfft_ctx* ctx, double* data, int n, int PH, int PW, int inverse) {
+    if (!ctx || !data || n < 0) return TFFT_E_INVALID;
+    int rc = check_dims(PH, PW);
+    if (rc) return rc;
+    if (n == 0) return TFFT_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->res_n = 0;
+    const size_t P = (size_t)PH * PW, pb = P * sizeof(double2);
+    size_t chunk = ctx->ws_limit / pb;
+    if (chunk < 1) chunk = 1;
+    if (chunk > (size_t)n) chunk = n;
+    Slot& S = ctx->slot[0];
+    if ((rc = ensure(ctx, S.spec, chunk * pb))) return rc;
+    Launcher L = make_launcher(ctx, S.stream);
+    for (size_t i0 = 0; i0 < (size_t)n; i0 += chunk) {
+        const size_t m = std::min(chunk, (size_t)n - i0);
+        CK(cudaMemcpyAsync(S.spec.p, data + i0 * P * 2, m * pb, cudaMemcpyHostToDevice, S.stream));
+        if ((rc = fft2d_planes(ctx, L, (double2*)S.spec.p, (int)m, PH, PW, inverse))) return rc;
+        CK(cudaMemcpyAsync(data + i0 * P * 2, S.spec.p, m * pb, cudaMemcpyDeviceToHost, S.stream));
+        CK(cudaStreamSynchronize(S.stream));
+    }
+    return TFFT_OK;
+}
+
+int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec, int n, int PH, int PW, double magmin,
+                             double rmin, double rmax, double* d_median, uint64_t* d_usable, void* stream) {
+    if (!ctx || !d_spec || n <= 0 || !d_median) return TFFT_E_INVALID;
+    int rc = check_dims(PH, PW);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    Slot& S = ctx->slot[1];
+    if ((rc = ensure(ctx, S.med, median_work_bytes(n * 3, CAND_CAP)))) return rc;
+    MedianWork mw;
+    median_work_carve(mw, S.med.p, n * 3, CAND_CAP);
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    const int m = std::min(PH, PW);
+    CK(launch_median_capacity(L, (const double2*)d_spec, n * 3, PH, PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
+    return TFFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,537 @@
+// tfft_kernels.cu -- sm_100a kernels of the TurtleFFT hot path: baseline FFT pass (v0),
+// median/capacity, embed scatter, extract gather+vote.
+// Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
+#include "tfft_kernels.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace tfft {
+
+#define TFFT_LAUNCH_CHECK(L)              \
+    do {                                  \
+        if ((L).launch_counter) ++*(L).launch_counter; \
+        cudaError_t e__ = cudaGetLastError(); \
+        if (e__ != cudaSuccess) return e__;   \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// Twiddles
+// --------------------------------------------------------------------------------------------
+cudaError_t build_twiddles(double2* d_tw, cudaStream_t s) {
+    std::vector<double2> h(TW_N / 2);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < TW_N / 2; k++) {
+        // exact octant symmetries keep cos/sin of k/TW_N consistent to the last bit
+        long double a = two_pi * (long double)k / (long double)TW_N;
+        h[k].x = (double)cosl(a);
+        h[k].y = (double)sinl(a);
+    }
+    h[0] = make_double2(1.0, 0.0);
+    h[TW_N / 4] = make_double2(0.0, 1.0);
+    cudaError_t e = cudaMemcpyAsync(d_tw, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+}
+
+// --------------------------------------------------------------------------------------------
+// Shared device helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// from_planes_u8 clamp8 (S:389): round() half away from zero, clamp to [0,255], cast.
+__device__ __forceinline__ uint8_t clamp8(double v) {
+    double r = round(v);
+    r = fmax(0.0, fmin(255.0, r));
+    return (uint8_t)r;
+}
+
+// --------------------------------------------------------------------------------------------
+// v0 FFT pass: one CTA transforms `cpc` pencils held entirely in shared memory with an
+// in-place radix-2 DIT (same butterfly order as fft1d S:341-358, but table twiddles).
+// Kept as the simple always-correct path and as the cross-check for the pencil kernels.
+// --------------------------------------------------------------------------------------------
+template <int IN, int OUT>
+__global__ void __launch_bounds__(512) fft_pass_v0(PassArgs a, int cpc) {
+    extern __shared__ double2 sm[];
+    const int n = 1 << a.log2n;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const long long q0 = (long long)blockIdx.x * cpc;  // first pencil of this CTA
+    const int len_other = a.axis == 0 ? a.PH : a.PW;   // pencils per plane
+    const int ip = (int)(q0 / len_other);              // plane index (image*3 + plane)
+    const int o0 = (int)(q0 % len_other);              // first row (axis 0) / column (axis 1)
+    double2* plane = a.spec + (size_t)ip * a.PH * a.PW;
+    const int img = ip / 3, ch = ip % 3;
+
+    if (a.axis == 0) {
+        // rows beyond out_rows are never consumed; rows beyond in_rows are all-zero on input
+        if (o0 >= a.out_rows) return;
+        if (o0 >= a.in_rows) {
+            if (OUT == OUT_C64)
+                for (int idx = tid; idx < cpc * n; idx += T) plane[(size_t)(o0 + idx / n) * a.PW + (idx % n)] = make_double2(0.0, 0.0);
+            return;
+        }
+    }
+
+    // ---- load, bit-reversed placement (S:343-345)
+    for (int idx = tid; idx < cpc * n; idx += T) {
+        int c, k;
+        if (a.axis == 0) { c = idx / n; k = idx % n; } else { c = idx % cpc; k = idx / cpc; }
+        double2 v;
+        if (IN == IN_U8) {
+            const int y = o0 + c;
+            double r = 0.0;
+            if (y < a.H && k < a.W) {
+                r = (double)a.img_in[((size_t)((size_t)img * a.H + y) * a.W + k) * 3 + ch];
+                if (a.center && ((k + y) & 1)) r = -r;  // apply_center S:392
+            }
+            v = make_double2(r, 0.0);
+        } else if (a.axis == 0) {
+            const int y = o0 + c;
+            v = (y < a.in_rows) ? plane[(size_t)y * a.PW + k] : make_double2(0.0, 0.0);
+        } else {
+            v = plane[(size_t)k * a.PW + o0 + c];
+        }
+        sm[c * n + (int)(__brev((unsigned)k) >> (32 - a.log2n))] = v;
+    }
+    __syncthreads();
+
+    // ---- butterflies
+    const int half_n = n >> 1;
+    for (int s = 1; s <= a.log2n; s++) {
+        const int half = 1 << (s - 1);
+        for (int b = tid; b < cpc * half_n; b += T) {
+            const int c = b >> (a.log2n - 1);
+            const int j = b & (half_n - 1);
+            const int jj = j & (half - 1);
+            const int pos = c * n + (((j >> (s - 1)) << s) | jj);
+            double2 w = a.tw[(size_t)jj << (TW_LOG2 - s)];
+            if (a.inverse) w.y = -w.y;
+            const double2 u = sm[pos];
+            const double2 v = cmul(sm[pos + half], w);
+            sm[pos] = make_double2(u.x + v.x, u.y + v.y);
+            sm[pos + half] = make_double2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+
+    // ---- store
+    const double scale = a.inverse ? 1.0 / (double)n : 1.0;  // S:357 (exact: n is a power of two)
+    for (int idx = tid; idx < cpc * n; idx += T) {
+        int c, k;
+        if (a.axis == 0) { c = idx / n; k = idx % n; } else { c = idx % cpc; k = idx / cpc; }
+        double2 v = sm[c * n + k];
+        v.x *= scale; v.y *= scale;
+        if (OUT == OUT_U8) {
+            const int y = o0 + c;
+            if (y < a.H && k < a.W) {
+                double r = v.x;                               // ifft_crop S:401 keeps the real part
+                if (a.center && ((k + y) & 1)) r = -r;        // S:1102
+                a.img_out[((size_t)((size_t)img * a.H + y) * a.W + k) * 3 + ch] = clamp8(r);
+            }
+        } else if (a.axis == 0) {
+            plane[(size_t)(o0 + c) * a.PW + k] = v;
+        } else {
+            plane[(size_t)k * a.PW + o0 + c] = v;
+        }
+    }
+}
+
+static cudaError_t launch_v0(const Launcher& L, const PassArgs& a) {
+    const int n = 1 << a.log2n;
+    const size_t per = (size_t)n * sizeof(double2);
+    const int other = a.axis == 0 ? a.PH : a.PW;
+    int cpc = 1;
+    // as many pencils per CTA as fit (columns: wider contiguous chunks; rows: more work per CTA)
+    const size_t budget = L.smem_optin < 200 * 1024 ? L.smem_optin : 200 * 1024;
+    while (cpc < 8 && (size_t)(cpc * 2) * per <= budget && other % (cpc * 2) == 0) cpc *= 2;
+    if (per * cpc > L.smem_optin) return cudaErrorInvalidConfiguration;
+    const size_t smem = per * cpc;
+    const long long npencils = (long long)a.nplanes * other;
+    const unsigned grid = (unsigned)(npencils / cpc);
+    void (*k)(PassArgs, int) = nullptr;
+    const int in = a.img_in ? IN_U8 : IN_C64, out = a.img_out ? OUT_U8 : OUT_C64;
+    if (in == IN_C64 && out == OUT_C64) k = fft_pass_v0<IN_C64, OUT_C64>;
+    else if (in == IN_U8 && out == OUT_C64) k = fft_pass_v0<IN_U8, OUT_C64>;
+    else if (in == IN_C64 && out == OUT_U8) k = fft_pass_v0<IN_C64, OUT_U8>;
+    else return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, 512, smem, L.stream>>>(a, cpc);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+
+cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& a, bool* handled);
+
+cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a) {
+    if (L.fft_impl != 0) {
+        bool handled = false;
+        cudaError_t e = launch_fft_pass_pencil(L, a, &handled);
+        if (e != cudaSuccess || handled) return e;
+    }
+    return launch_v0(L, a);
+}
+
+// --------------------------------------------------------------------------------------------
+// Median of |F| (median_abs S:404-409): exact selection of the element of rank P/2 by an MSB
+// radix select on the IEEE bit pattern of hypot(re,im) (non-negative doubles order like
+// unsigned integers).  Two 11-bit histogram passes narrow the key to a 22-bit prefix; the
+// survivors are compacted and finished by one CTA per plane.  If the survivors do not fit
+// (degenerate spectra with massively repeated magnitudes) further full histogram passes run.
+// --------------------------------------------------------------------------------------------
+constexpr int RADIX_BITS = 11;
+constexpr int RADIX = 1 << RADIX_BITS;
+// digit d (0 = most significant) covers key bits [63-11d-1 .. 63-11d-11] of the 63 value bits
+__device__ __forceinline__ int key_shift(int d) { int s = 63 - RADIX_BITS * (d + 1); return s < 0 ? 0 : s; }
+__device__ __forceinline__ int key_width(int d) { int s = 63 - RADIX_BITS * (d + 1); return s < 0 ? RADIX_BITS + s : RADIX_BITS; }
+constexpr int NUM_DIGITS = 6;  // 5*11 + 8 = 63
+
+__device__ __forceinline__ uint64_t mag_key(double2 z) {
+    return (uint64_t)__double_as_longlong(hypot(z.x, z.y));  // std::abs(complex) S:406
+}
+
+size_t median_work_bytes(int nplanes, uint32_t cand_cap) {
+    size_t b = 0;
+    b += (size_t)nplanes * RADIX * sizeof(uint32_t);
+    b += (size_t)nplanes * sizeof(uint64_t) * 3;  // prefix, rank, counts
+    b += (size_t)nplanes * cand_cap * sizeof(uint64_t);
+    b += (size_t)(nplanes + 4) * sizeof(uint32_t);  // cand_n + fallback flag
+    return (b + 255) & ~(size_t)255;
+}
+void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap) {
+    char* p = (char*)base;
+    w.prefix = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
+    w.rank = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
+    w.counts = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
+    w.cand = (uint64_t*)p; p += (size_t)nplanes * cand_cap * sizeof(uint64_t);
+    w.hist = (uint32_t*)p; p += (size_t)nplanes * RADIX * sizeof(uint32_t);
+    w.cand_n = (uint32_t*)p;
+    w.cand_cap = cand_cap;
+}
+
+__global__ void median_init(MedianWork w, int nplanes, uint64_t P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nplanes * RADIX) w.hist[i] = 0;
+    if (i < nplanes) { w.prefix[i] = 0; w.rank[i] = P / 2; w.cand_n[i] = 0; w.counts[i] = 0; }
+}
+
+// histogram of digit d over keys whose higher digits equal prefix; grid = (chunks, nplanes)
+__global__ void __launch_bounds__(512) median_hist(const double2* __restrict__ spec, uint64_t P, int d, MedianWork w, const int* gate) {
+    __shared__ uint32_t sh[RADIX];
+    if (gate && !*gate) return;  // degenerate-spectrum fallback not needed
+    const int ip = blockIdx.y;
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const double2* pl = spec + (size_t)ip * P;
+    const int sft = key_shift(d), wid = key_width(d);
+    const uint64_t prefix = w.prefix[ip];
+    const int hi_sft = sft + wid;  // bits above this digit
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = mag_key(pl[i]);
+        if (d == 0 || (k >> hi_sft) == (prefix >> hi_sft))
+            atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&w.hist[ip * RADIX + i], sh[i]);
+}
+
+// one CTA per plane: find the bucket holding the wanted rank, extend prefix, clear histogram
+__global__ void median_pick(int d, MedianWork w, const int* gate) {
+    if (gate && !*gate) return;
+    const int ip = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint64_t r = w.rank[ip];
+        uint32_t* h = w.hist + ip * RADIX;
+        const int wid = key_width(d);
+        int b = 0;
+        for (; b < (1 << wid) - 1; b++) {
+            if (r < h[b]) break;
+            r -= h[b];
+        }
+        w.rank[ip] = r;
+        w.prefix[ip] |= (uint64_t)b << key_shift(d);
+        if (!gate) w.cand_n[ip] = h[b];  // survivors after this digit
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) w.hist[ip * RADIX + i] = 0;
+}
+
+// compact the keys matching the first `d` digits (only if they fit cand_cap)
+__global__ void __launch_bounds__(512) median_compact(const double2* __restrict__ spec, uint64_t P, int d, MedianWork w, uint32_t* fill) {
+    const int ip = blockIdx.y;
+    if (w.cand_n[ip] > w.cand_cap) return;
+    const double2* pl = spec + (size_t)ip * P;
+    const int hi_sft = key_shift(d - 1);
+    const uint64_t prefix = w.prefix[ip] >> hi_sft;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = mag_key(pl[i]);
+        if ((k >> hi_sft) == prefix) {
+            uint32_t slot = atomicAdd(&fill[ip], 1u);
+            if (slot < w.cand_cap) w.cand[(size_t)ip * w.cand_cap + slot] = k;
+        }
+    }
+}
+
+// finish on the compacted list: one CTA per plane runs the remaining digits locally.
+__global__ void __launch_bounds__(1024) median_finish(int d0, MedianWork w, double* median) {
+    __shared__ uint32_t sh[RADIX];
+    __shared__ uint64_t s_prefix, s_rank;
+    const int ip = blockIdx.x;
+    const uint32_t n = w.cand_n[ip];
+    if (n > w.cand_cap) return;  // handled by the full-pass fallback
+    const uint64_t* c = w.cand + (size_t)ip * w.cand_cap;
+    if (threadIdx.x == 0) { s_prefix = w.prefix[ip]; s_rank = w.rank[ip]; }
+    for (int d = d0; d < NUM_DIGITS; d++) {
+        for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
+        __syncthreads();
+        const int sft = key_shift(d), wid = key_width(d), hi_sft = sft + wid;
+        const uint64_t prefix = s_prefix;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t k = c[i];
+            if ((k >> hi_sft) == (prefix >> hi_sft)) atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint64_t r = s_rank;
+            int b = 0;
+            for (; b < (1 << wid) - 1; b++) {
+                if (r < sh[b]) break;
+                r -= sh[b];
+            }
+            s_rank = r;
+            s_prefix = prefix | ((uint64_t)b << sft);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) median[ip] = __longlong_as_double((long long)s_prefix);
+}
+
+// fallback completion when the survivors did not fit: prefix is complete after all digits
+__global__ void median_from_prefix(MedianWork w, double* median, int nplanes, const int* gate) {
+    if (!*gate) return;
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip < nplanes) median[ip] = __longlong_as_double((long long)w.prefix[ip]);  // exact for every plane
+}
+__global__ void any_overflow(MedianWork w, int nplanes, int* flag) {
+    int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip < nplanes && w.cand_n[ip] > w.cand_cap) *flag = 1;
+}
+
+// Capacity count (S:999-1007): annulus bins in index space (radius from bin (0,0), scaled by
+// min(PH,PW)), off the axes (on_axis S:698), |F| >= magmin*median, conjugate distinct.
+// Only the quarter-disc y,x <= rhi can satisfy the radius test, so only that box is scanned.
+__global__ void __launch_bounds__(256) capacity_count(const double2* __restrict__ spec, int PH, int PW, int ymax, int xmax,
+                                                      double rlo, double rhi, double magmin,
+                                                      const double* __restrict__ median, uint64_t* counts) {
+    const int ip = blockIdx.y;
+    const double thr = magmin * median[ip];
+    const double2* pl = spec + (size_t)ip * PH * PW;
+    const long long box = (long long)(ymax + 1) * (xmax + 1);
+    unsigned local = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < box; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(i / (xmax + 1)), x = (int)(i % (xmax + 1));
+        if (y == 0 || x == 0 || y == PH / 2 || x == PW / 2) continue;  // PH, PW are even powers of two
+        const double r = sqrt((double)((long long)y * y + (long long)x * x));  // == hypot for exact integer sums
+        if (r < rlo || r > rhi) continue;
+        const double2 z = pl[(size_t)y * PW + x];
+        if (hypot(z.x, z.y) < thr) continue;
+        local++;  // conjugate (PH-y, PW-x) != (y,x) is implied by the axis test
+    }
+    // warp + block reduce
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    __shared__ unsigned ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += ws[i];
+        if (t) atomicAdd((unsigned long long*)&counts[ip], (unsigned long long)t);
+    }
+}
+__global__ void capacity_finish(const uint64_t* counts, uint64_t* usable, int nimg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nimg) usable[i] = counts[3 * i] / 2 + counts[3 * i + 1] / 2 + counts[3 * i + 2] / 2;  // S:1006, S:1008
+}
+
+cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, int PH, int PW,
+                                   double magmin, double rlo, double rhi, MedianWork w,
+                                   double* d_median, uint64_t* d_usable) {
+    const uint64_t P = (uint64_t)PH * PW;
+    const int chunks = (int)((P + 512ull * 16 - 1) / (512ull * 16));
+    const dim3 grid((unsigned)(chunks > 592 ? 592 : chunks), (unsigned)nplanes);
+    median_init<<<(nplanes * RADIX + 255) / 256, 256, 0, L.stream>>>(w, nplanes, P);
+    TFFT_LAUNCH_CHECK(L);
+    // two full histogram passes -> 22-bit prefix
+    for (int d = 0; d < 2; d++) {
+        median_hist<<<grid, 512, 0, L.stream>>>(spec, P, d, w, nullptr);
+        TFFT_LAUNCH_CHECK(L);
+        median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, nullptr);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    // compaction of the survivors + local finish.  `fill` reuses counts[] storage (uint32 view)
+    // before the capacity kernel needs it; it is re-zeroed afterwards.
+    uint32_t* fill = (uint32_t*)w.counts;
+    median_compact<<<grid, 512, 0, L.stream>>>(spec, P, 2, w, fill);
+    TFFT_LAUNCH_CHECK(L);
+    median_finish<<<nplanes, 1024, 0, L.stream>>>(2, w, d_median);
+    TFFT_LAUNCH_CHECK(L);
+    // Degenerate fallback (survivors > cand_cap, e.g. flat images whose spectrum is all zeros):
+    // finish every plane with full histogram passes.  The decision stays on the device -- the
+    // extra kernels are gated by a flag and exit immediately in the normal case (no host sync).
+    {
+        int* d_flag = (int*)(w.cand_n + nplanes);  // one spare word after cand_n (see median_work_bytes)
+        cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), L.stream);
+        if (e != cudaSuccess) return e;
+        any_overflow<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, nplanes, d_flag);
+        TFFT_LAUNCH_CHECK(L);
+        for (int d = 2; d < NUM_DIGITS; d++) {
+            median_hist<<<grid, 512, 0, L.stream>>>(spec, P, d, w, d_flag);
+            TFFT_LAUNCH_CHECK(L);
+            median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, d_flag);
+            TFFT_LAUNCH_CHECK(L);
+        }
+        median_from_prefix<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, d_median, nplanes, d_flag);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
+    if (e != cudaSuccess) return e;
+    if (d_usable) {
+        const int m = PH < PW ? PH : PW;
+        (void)m;
+        int ymax = (int)floor(rhi), xmax = (int)floor(rhi);
+        if (ymax > PH - 1) ymax = PH - 1;
+        if (xmax > PW - 1) xmax = PW - 1;
+        if (ymax < 0) ymax = 0;
+        if (xmax < 0) xmax = 0;
+        const long long box = (long long)(ymax + 1) * (xmax + 1);
+        int cb = (int)((box + 256 * 8 - 1) / (256 * 8));
+        if (cb > 1184) cb = 1184;
+        if (cb < 1) cb = 1;
+        capacity_count<<<dim3((unsigned)cb, (unsigned)nplanes), 256, 0, L.stream>>>(spec, PH, PW, ymax, xmax, rlo, rhi, magmin, d_median, w.counts);
+        TFFT_LAUNCH_CHECK(L);
+        capacity_finish<<<(nplanes / 3 + 255) / 256, 256, 0, L.stream>>>(w.counts, d_usable, nplanes / 3);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    return cudaSuccess;
+}
+
+// --------------------------------------------------------------------------------------------
+// Embed scatter (write_bit_on_bin S:712-732): |F| kept (floored at 1e-12), phase set to
+// +-alpha (+ jitter), conjugate bin mirrored so the plane stays real.  Bins are unique and
+// never alias a conjugate (Turtle::mark_here S:805-809), so the scatter is conflict-free.
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_scatter(double2* spec, int PH, int PW, const uint32_t* __restrict__ bins,
+                                                     const uint8_t* __restrict__ bits, size_t nbits,
+                                                     const double* __restrict__ jitter, double alpha,
+                                                     double cos_a, double sin_a, const uint64_t* __restrict__ usable) {
+    const int img = blockIdx.y;
+    if (usable && usable[img] < (uint64_t)nbits) return;  // S:1009: over capacity -> image untouched
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbits) return;
+    const uint32_t b = bins[i];
+    const int p = (int)(b >> 30);
+    const uint32_t lin = b & 0x3FFFFFFFu;
+    const int y = (int)(lin / (uint32_t)PW), x = (int)(lin % (uint32_t)PW);
+    double2* pl = spec + (size_t)(img * 3 + p) * PH * PW;
+    const double2 z = pl[lin];
+    const double mag = fmax(1e-12, hypot(z.x, z.y));
+    const int bit = bits[(size_t)img * nbits + i];
+    double c, s;
+    if (jitter) {
+        const double theta = (bit ? alpha : -alpha) + jitter[i];
+        sincos(theta, &s, &c);
+    } else {
+        c = cos_a;                 // cos(-a) == cos(a), sin(-a) == -sin(a) exactly
+        s = bit ? sin_a : -sin_a;
+    }
+    const double2 nv = make_double2(mag * c, mag * s);  // std::polar(mag, theta)
+    const int cy = (PH - y) % PH, cx = (PW - x) % PW;   // conj_idx S:370-372
+    if (cy == y && cx == x) {
+        pl[lin] = make_double2(mag, 0.0);  // S:727
+    } else {
+        pl[lin] = nv;
+        pl[(size_t)cy * PW + cx] = make_double2(nv.x, -nv.y);
+    }
+}
+
+cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, int PH, int PW,
+                         const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
+                         double alpha, double cos_a, double sin_a, const uint64_t* usable) {
+    if (nbits == 0 || nimg == 0) return cudaSuccess;
+    dim3 grid((unsigned)((nbits + 255) / 256), (unsigned)nimg);
+    embed_scatter<<<grid, 256, 0, L.stream>>>(spec, PH, PW, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+
+// --------------------------------------------------------------------------------------------
+// Extract (read_bit_from_bin S:734-746 restated in full so ties behave like the reference,
+// rep3/rep7 majority S:468-474 / S:501-508, MSB-first packing S:447-454).
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ang_diff(double a, double b) {
+    const double PI = 3.14159265358979323846;
+    double d = fmod(a - b + PI, 2 * PI);
+    if (d < 0) d += 2 * PI;
+    return fabs(d - PI);
+}
+__device__ __forceinline__ int read_bit(double2 z, double alpha, double jit) {
+    const double th = atan2(z.y, z.x);
+    return ang_diff(th, jit + alpha) <= ang_diff(th, jit - alpha) ? 1 : 0;
+}
+__device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, int img, size_t P, uint32_t b) {
+    return spec[(size_t)(img * 3 + (int)(b >> 30)) * P + (b & 0x3FFFFFFFu)];
+}
+
+__global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ spec, size_t P, const uint32_t* __restrict__ bins,
+                                                   size_t nbins, const double* __restrict__ jitter, double alpha,
+                                                   uint8_t* raw_bits) {
+    const int img = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbins) return;
+    raw_bits[(size_t)img * nbins + i] = (uint8_t)read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
+}
+
+// one thread per decoded bit; a warp packs 32 decoded bits into 4 bytes with a ballot
+__global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ spec, size_t P, const uint32_t* __restrict__ bins,
+                                                    size_t ndec, int rep, const double* __restrict__ jitter, double alpha,
+                                                    uint8_t* out_bytes, size_t nbytes) {
+    const int img = blockIdx.y;
+    const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bit = 0;
+    if (d < ndec) {
+        int s = 0;
+        for (int j = 0; j < rep; j++) {
+            const size_t i = d * rep + j;
+            s += read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
+        }
+        bit = (s >= rep / 2 + 1) ? 1 : 0;  // >=2 of 3, >=4 of 7 (rep 1: the bit itself)
+    }
+    const unsigned m = __brev(__ballot_sync(0xffffffffu, bit));  // lane 0 -> MSB (bytes_from_bits S:450)
+    const int lane = threadIdx.x & 31;
+    const size_t byte0 = (d - lane) / 8;
+    if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
+}
+
+cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
+                           const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
+                           uint8_t* out_bytes, uint8_t* raw_bits) {
+    if (nimg == 0) return cudaSuccess;
+    const size_t P = (size_t)PH * PW;
+    if (raw_bits && nbins) {
+        extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    const size_t ndec = nbins / (size_t)rep;
+    const size_t nbytes = (ndec + 7) / 8;
+    if (out_bytes && nbytes) {
+        extract_vote<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, ndec, rep, jitter, alpha, out_bytes, nbytes);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    return cudaSuccess;
+}
+
+}  // namespace tfft

@@ -1,0 +1,74 @@
+// tfft_kernels.cuh -- device-side interface of the TurtleFFT hot path (sm_100a).
+// Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfft {
+
+// Twiddle table: tw[k] = exp(+2*pi*i*k / TW_N), k in [0, TW_N/2).  The reference's forward
+// transform uses the +i sign (S:347); inverse passes conjugate on the fly.
+constexpr int TW_LOG2 = 14;  // 16384 = TFFT_MAX_DIM
+constexpr int TW_N = 1 << TW_LOG2;
+
+enum PassIn { IN_C64 = 0, IN_U8 = 1 };
+enum PassOut { OUT_C64 = 0, OUT_U8 = 1 };
+
+// One 1-D FFT pass over a batch of planes.  A "pencil" is one row (axis 0) or one column
+// (axis 1) of one padded plane; planes are [PH][PW] complex<double>, nplanes = 3 * nimages.
+struct PassArgs {
+    double2* spec;           // [nplanes][PH][PW]
+    const uint8_t* img_in;   // IN_U8 : [n][H][W][3]  (to_planes_u8 S:383 + pad_to_fft S:393 fused)
+    uint8_t* img_out;        // OUT_U8: [n][H][W][3]  (ifft_crop S:399 + from_planes_u8 S:387 fused)
+    const double2* tw;       // twiddle table (device)
+    const uint64_t* usable;  // OUT_U8 only, may be null (unused by the pass itself)
+    int nplanes;
+    int W, H, PW, PH;
+    int log2n;    // pencil length = 1 << log2n
+    int axis;     // 0: along x (rows), 1: along y (columns)
+    int inverse;  // 0: e^{+i} (reference forward), 1: e^{-i} and scale by 1/n (S:357)
+    int center;   // apply_center S:392 on the image side of IN_U8 / OUT_U8
+    // Zero-structure hints (never change results, only skip work on known-zero data):
+    int in_rows;  // axis 0, IN_C64/IN_U8: rows y >= in_rows are known to be all-zero on input
+    int out_rows; // axis 0, OUT_*: rows y >= out_rows need not be produced
+};
+
+struct Launcher {
+    cudaStream_t stream;
+    uint64_t* launch_counter;  // host-side counter of kernels launched
+    int sm_count;
+    size_t smem_optin;
+    int fft_impl;  // 0 = v0 (simple shared-memory radix-2), 1 = pencil kernels
+};
+
+cudaError_t build_twiddles(double2* d_tw, cudaStream_t s);  // fills TW_N/2 entries
+cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a);
+
+// ---- median + capacity (median_abs S:404-409, count_plane S:999-1007) ----------------------
+struct MedianWork {
+    uint32_t* hist;      // [nplanes][2048]
+    uint64_t* prefix;    // [nplanes] key prefix selected so far
+    uint64_t* rank;      // [nplanes] remaining rank inside the prefix bucket
+    uint64_t* cand;      // [nplanes][cand_cap] candidate keys
+    uint32_t* cand_n;    // [nplanes]
+    uint32_t cand_cap;
+    uint64_t* counts;    // [nplanes] capacity counts before halving
+};
+size_t median_work_bytes(int nplanes, uint32_t cand_cap);
+void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);
+// d_median: [nplanes]; d_usable: [nplanes/3] (sum over the 3 planes of count/2)
+cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, int PH, int PW,
+                                   double magmin, double rlo, double rhi, MedianWork w,
+                                   double* d_median, uint64_t* d_usable);
+
+// ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
+cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, int PH, int PW,
+                         const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
+                         double alpha, double cos_a, double sin_a, const uint64_t* usable);
+
+// ---- extract gather + vote (read_bit_from_bin S:734-746, rep3/7 S:468/S:501, pack S:447) --
+cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
+                           const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
+                           uint8_t* out_bytes, uint8_t* raw_bits);
+
+}  // namespace tfft

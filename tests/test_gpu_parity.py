@@ -1,0 +1,270 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the
+oracle (oracle/_ref when shipped, else the C port) and the committed golden fixtures.
+
+Bars: integer/byte outputs (raw bits, decoded bytes, usable) bit-exact; spectra max|d|/rms <= 1e-9
+(BASELINE.json) -- asserted at 1e-11, two orders tighter; stego pixels <= 1 LSB and >= 99.99 % equal.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from steganosaurus_b200 import synth
+import steganosaurus_b200 as sb
+from util import golden_cases, load_golden, spec_err
+
+pytestmark = pytest.mark.gpu
+
+SPEC_TOL = 1e-11   # north_star allows 1e-9 relative
+PIX_EQ = 0.9999
+
+
+def oracle():
+    return O.best()
+
+
+def assert_pixels(a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    assert d.max() <= 1, f"max pixel diff {d.max()}"
+    assert (d == 0).mean() >= PIX_EQ, f"only {(d == 0).mean():.6f} equal"
+
+
+@pytest.mark.parametrize("PH,PW,n", [(16, 16, 3), (32, 64, 2), (64, 16, 1), (128, 128, 4), (512, 512, 2), (256, 1024, 1),
+                                     (2048, 512, 1), (4096, 64, 1), (64, 8192, 1)])
+def test_fft2d_matches_oracle(ctx, PH, PW, n):
+    rng = np.random.default_rng(PH * 31 + PW)
+    a = rng.standard_normal((n, PH, PW)) + 1j * rng.standard_normal((n, PH, PW))
+    o = oracle()
+    for inv in (False, True):
+        got = ctx.fft2d(a, inverse=inv)
+        want = np.stack([o.fft2d(a[i], inv) for i in range(n)])
+        e = spec_err(got, want)
+        assert e[0] < SPEC_TOL and e[1] < 1e-13, (PH, PW, inv, e)
+    # round trip is the identity
+    back = ctx.fft2d(ctx.fft2d(a), inverse=True)
+    assert np.abs(back - a).max() < 1e-12
+
+
+def test_fft2d_known_answer(ctx):
+    A = np.zeros((1, 16, 16), np.complex128)
+    A[0, 0, 1] = 1.0  # delta at x=1 -> e^{+2 pi i k/16} along x (forward is e^{+i}, S:347)
+    F = ctx.fft2d(A)[0]
+    k = np.arange(16)
+    assert np.allclose(F, np.exp(2j * np.pi * k / 16)[None, :].repeat(16, 0), atol=1e-14)
+
+
+@pytest.mark.parametrize("W,H,center", [(64, 48, False), (100, 60, True), (512, 512, False), (300, 1000, True)])
+def test_forward_spectrum(ctx, W, H, center):
+    img = synth.gen_texture(W, H, W * 7 + H)
+    got = ctx.forward_spectrum(img, center)
+    want = oracle().forward_spectrum(img, center)
+    e = spec_err(got, want)
+    assert e[0] < SPEC_TOL and e[1] < 1e-13, e
+    # Hermitian symmetry of a real plane's spectrum
+    conj = np.conj(np.roll(np.flip(got, (1, 2)), 1, (1, 2)))
+    assert np.abs(got - conj).max() / np.abs(got).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_embed_extract(ctx, name):
+    g = load_golden(name)
+    stego, usable, med = ctx.embed_batch(g["cover"][None], g["bins"], g["bits"][None], g["alpha"], g["center"],
+                                         0.01, g["rmin"], g["rmax"])
+    assert int(usable[0]) == g["usable"]
+    assert np.allclose(med[0], g["medians"], rtol=1e-11)
+    assert_pixels(stego[0], g["stego"])
+    # extraction from the REFERENCE's stego: raw bits and decoded bytes bit-exact
+    dec1, raw = ctx.extract_bits(g["stego"][None], g["bins"], 1, g["alpha"], g["center"])
+    assert np.array_equal(raw[0], g["raw_all"])
+    assert np.array_equal(dec1[0], np.packbits(g["raw_all"]))
+    dec3, _ = ctx.extract_bits(g["stego"][None], g["bins"][: g["hdr_n"]], 3, g["alpha"], g["center"])
+    assert np.array_equal(dec3[0], g["dec3"])
+    rest = g["bins"][g["hdr_n"]:]
+    dec7, _ = ctx.extract_bits(g["stego"][None], rest[: rest.size // 7 * 7], 7, g["alpha"], g["center"])
+    assert np.array_equal(dec7[0], g["dec7"])
+    sy, sx = g["spec_sample_yx"]
+    F = ctx.forward_spectrum(g["cover"], g["center"])
+    rms = np.sqrt(np.mean(np.abs(F) ** 2))
+    assert np.abs(F[:, sy, sx] - g["spec_sample"]).max() / rms < SPEC_TOL
+
+
+@pytest.mark.parametrize("W,H,nbits,center,alpha", [
+    (256, 256, 2480, False, 0.5), (512, 512, 60000, False, 0.5), (500, 300, 5000, True, 0.3),
+    (1024, 512, 30000, False, 0.18), (640, 480, 8000, False, 0.5)])
+def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
+    o = oracle()
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    cover = synth.gen_texture(W, H, W + 3 * H)
+    bins = synth.random_bins(PH, PW, nbits, 11)
+    bits = synth.random_bits(1, nbits, 12)
+    want = o.embed(cover, bins, bits[0], alpha, center)
+    stego, usable, med = ctx.embed_batch(cover[None], bins, bits, alpha, center)
+    assert int(usable[0]) == want["usable"]
+    assert np.allclose(med[0], want["medians"], rtol=1e-11)
+    assert_pixels(stego[0], want["stego"])
+    for rep in (1, 3, 7):
+        nb = nbits // rep * rep
+        dec, raw = ctx.extract_bits(want["stego"][None], bins[:nb], rep, alpha, center)
+        wdec, wraw = o.extract(want["stego"], bins[:nb], rep, alpha, center)
+        assert np.array_equal(raw[0], wraw)
+        assert np.array_equal(dec[0], wdec)
+
+
+def test_batch_chunking_and_independence(ctx):
+    """Every image has its own bits; a tiny workspace forces several chunks and both slots."""
+    W = H = 128
+    n, nbits = 7, 900
+    covers = np.stack([synth.gen_texture(W, H, 100 + i) for i in range(n)])
+    bins = synth.random_bins(H, W, nbits, 3)
+    bits = synth.random_bits(n, nbits, 4)
+    ctx.set_workspace_limit(2 * 2 * 3 * H * W * 16)  # two images per slot
+    try:
+        stego, usable, med = ctx.embed_batch(covers, bins, bits)
+        dec, raw = ctx.extract_bits(stego, bins, 3)
+    finally:
+        ctx.set_workspace_limit(40 << 30)
+    o = oracle()
+    for i in range(n):
+        want = o.embed(covers[i], bins, bits[i])
+        assert_pixels(stego[i], want["stego"])
+        assert int(usable[i]) == want["usable"]
+        wdec, wraw = o.extract(stego[i], bins, 3)
+        assert np.array_equal(raw[i], wraw) and np.array_equal(dec[i], wdec)
+
+
+def test_two_phase_extract(ctx):
+    g = load_golden("g512_walk")
+    ctx.forward_batch(g["stego"][None], g["center"])
+    dec3, raw3 = ctx.read_bits(g["bins"][:912], 3, g["alpha"])
+    assert np.array_equal(dec3[0], g["dec3"])
+    rest = g["bins"][912:]
+    dec7, raw7 = ctx.read_bits(rest[: rest.size // 7 * 7], 7, g["alpha"])
+    assert np.array_equal(dec7[0], g["dec7"])
+    assert np.array_equal(np.concatenate([raw3[0], raw7[0]]), g["raw_all"][: 912 + rest.size // 7 * 7])
+
+
+def test_capacity_error_and_passthrough(ctx):
+    """S:1009-1012: nbits > usable -> error with the same counts; the image passes through unmodified."""
+    cover = synth.gen_cover(256, 256, 5)
+    nbits = 24208  # the reference's own '400-byte secret into 256^2' case
+    bins = synth.random_bins(256, 256, nbits, 1)
+    bits = synth.random_bits(1, nbits, 2)
+    with pytest.raises(sb.CapacityError) as ei:
+        ctx.embed_batch(cover[None], bins, bits)
+    want = oracle().embed(cover, bins, bits[0])
+    assert int(ei.value.usable[0]) == want["usable"] == 15288
+    assert "Need 24208 bits (after ECC), capacity ~15288 bits." in str(ei.value)
+    assert np.array_equal(ei.value.stego[0], cover)
+
+
+def test_degenerate_flat_image(ctx):
+    """Constant image: |F| is zero almost everywhere -> massively tied magnitudes (median fallback path)."""
+    cover = np.full((64, 64, 3), 77, np.uint8)
+    nbits = 200
+    bins = synth.random_bins(64, 64, nbits, 1)
+    bits = synth.random_bits(1, nbits, 2)
+    want = oracle().embed(cover, bins, bits[0])
+    stego, usable, med = ctx.embed_batch(cover[None], bins, bits)
+    assert int(usable[0]) == want["usable"]
+    assert np.allclose(med[0], want["medians"], atol=1e-9)
+    assert_pixels(stego[0], want["stego"])
+
+
+def test_read_ties(ctx):
+    """read_bit_from_bin ties -> 1: a flat image has exact zeros in the annulus."""
+    cover = np.zeros((32, 32, 3), np.uint8)
+    bins = synth.random_bins(32, 32, 60, 1)
+    dec, raw = ctx.extract_bits(cover[None], bins, 1)
+    assert raw.min() == 1
+
+
+def test_jitter_hook(ctx):
+    """Optional per-bin phase jitter (KS::jitter S:690): embed at +-alpha + j, read around j."""
+    W = H = 256
+    nbits = 3000
+    cover = synth.gen_cover(W, H, 9)
+    bins = synth.random_bins(H, W, nbits, 5)
+    bits = synth.random_bits(1, nbits, 6)
+    jit = np.random.default_rng(7).uniform(-0.05, 0.05, nbits)
+    stego, _, _ = ctx.embed_batch(cover[None], bins, bits, jitter=jit)
+    dec, raw = ctx.extract_bits(stego, bins, 1, jitter=jit)
+    assert (raw[0] != bits[0]).mean() < 0.02
+
+
+def test_empty_inputs(ctx):
+    cover = synth.gen_cover(64, 64, 1)
+    stego, usable, med = ctx.embed_batch(cover[None], np.zeros(0, np.uint32), np.zeros((1, 0), np.uint8))
+    assert_pixels(stego[0], cover)  # nothing embedded: round trip of the cover
+    assert np.array_equal(stego[0], cover)
+    dec, raw = ctx.extract_bits(cover[None], np.zeros(0, np.uint32), 3)
+    assert dec.shape == (1, 0)
+    s0, u0, m0 = ctx.embed_batch(np.zeros((0, 64, 64, 3), np.uint8), np.zeros(0, np.uint32), np.zeros((0, 0), np.uint8))
+    assert s0.shape[0] == 0
+    with pytest.raises(sb.TfftError):
+        ctx.embed_batch(cover[None], np.array([3 << 30], np.uint32), np.zeros((1, 1), np.uint8))  # plane 3
+    with pytest.raises(sb.TfftError):
+        ctx.extract_bits(cover[None], np.zeros(4, np.uint32), 5)  # rep 5 is dead code upstream (S:477)
+
+
+def test_device_pointer_api(ctx):
+    import torch
+    W, H, n, nbits = 320, 200, 3, 4000
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    covers = np.stack([synth.gen_texture(W, H, 40 + i) for i in range(n)])
+    bins = synth.random_bins(PH, PW, nbits, 3)
+    bits = synth.random_bits(n, nbits, 4)
+    hs, hu, hm = ctx.embed_batch(covers, bins, bits)
+    dev = torch.device("cuda:0")
+    d_cover = torch.from_numpy(covers).to(dev)
+    d_bins = torch.from_numpy(bins.astype(np.int64)).to(dev).to(torch.int32) if False else torch.from_numpy(bins.view(np.int32)).to(dev)
+    d_bits = torch.from_numpy(bits).to(dev)
+    d_stego = torch.empty_like(d_cover)
+    d_us = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_med = torch.zeros(n, 3, dtype=torch.float64, device=dev)
+    ctx.embed_batch_dev(d_cover, d_bins, d_bits, d_stego, usable=d_us, median=d_med)
+    d_out = torch.zeros(n, (nbits // 7 + 7) // 8, dtype=torch.uint8, device=dev)
+    d_raw = torch.zeros(n, nbits // 7 * 7, dtype=torch.uint8, device=dev)
+    ctx.extract_bits_dev(d_stego, d_bins[: nbits // 7 * 7], 7, d_out, d_raw)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_stego.cpu().numpy(), hs)
+    assert np.array_equal(d_us.cpu().numpy().astype(np.uint64), hu)
+    assert np.array_equal(d_med.cpu().numpy(), hm)
+    dec, raw = ctx.extract_bits(hs, bins[: nbits // 7 * 7], 7)
+    assert np.array_equal(d_out.cpu().numpy(), dec) and np.array_equal(d_raw.cpu().numpy(), raw)
+
+
+def test_full_size_roundtrip_properties(ctx):
+    """BASELINE sizes, size-independent properties: at pow2 4096^2 with a 30 720-byte frame
+    (1 722 128 bins) embed -> extract recovers every voted bit; forward o inverse is the identity."""
+    W = H = 4096
+    nbits = synth.frame_len(30720)
+    assert nbits == 1722128
+    cover = synth.gen_cover(W, H, 1000)
+    bins = synth.random_bins(H, W, nbits, 21)
+    bits1 = synth.random_bits(1, 304 + 8 * (30720 + 16), 22)[0]
+    bits = np.concatenate([np.repeat(bits1[:304], 3), np.repeat(bits1[304:], 7)])[None]
+    stego, usable, med = ctx.embed_batch(cover[None], bins, bits)
+    assert int(usable[0]) == 3950328  # SURVEY section 6.2, last row
+    assert abs(med[0, 0] - 19664.9) / 19664.9 < 0.05
+    d3, raw3 = ctx.extract_bits(stego, bins[:912], 3)
+    d7, raw7 = ctx.extract_bits(stego, bins[912:], 7)
+    assert np.array_equal(d3[0], np.packbits(bits1[:304]))
+    assert np.array_equal(d7[0], np.packbits(bits1[304:]))
+    ber = (np.concatenate([raw3[0], raw7[0]]) != bits[0]).mean()
+    assert ber < 0.02, ber
+    # nothing embedded -> exact identity on pixels
+    s0, _, _ = ctx.embed_batch(cover[None], bins[:0], bits[:, :0])
+    assert np.array_equal(s0[0], cover)
+
+
+def test_uhd_matches_reference_failure_mode(ctx):
+    """3840x2160 pads to 4096^2 and the crop destroys the signal: the REFERENCE's own extract fails
+    (SURVEY fact 3).  Parity here = same stego pixels / raw bits as the oracle on a small analogue,
+    and a high raw BER on the full UHD size just like upstream."""
+    W, H = 3840, 2160
+    nbits = 60000
+    cover = synth.gen_cover(W, H, 1001)
+    bins = synth.random_bins(4096, 4096, nbits, 5)
+    bits = synth.random_bits(1, nbits, 6)
+    stego, usable, _ = ctx.embed_batch(cover[None], bins, bits)
+    _, raw = ctx.extract_bits(stego, bins, 1)
+    assert (raw[0] != bits[0]).mean() > 0.05
