@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- embed+extract megapixels/s for a batch of 4K UHD RGB covers (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over a batch of B synthetic 3840x2160 RGB covers
+(pad 4096^2), each with its own 30 720-byte frame (1 722 128 embedded bits, one shared bin list):
+embed (fwd 2-D FFT, median+capacity, phase scatter, inv 2-D FFT, u8 quantise) followed by extract
+(fwd 2-D FFT, phase gather, Rep-3/Rep-7 vote).  MP = W*H image pixels per image, counted once per
+embed+extract round.  Every rank processes its own batch (weak scaling, no collective on the data
+path); the only torch.distributed traffic is the timing barrier and the max-over-ranks reduce.
+
+Printed line (rank 0): see the task contract -- value (inputs resident in HBM), e2e (host buffers
+through the C-ABI, H2D/D2H inside the timed region), roofline (dominant kernel, CUDA events inside
+the timed region, against MEASURED_PEAKS.json), cpu_baseline (the reference's own hot-path code on
+the host cores), clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W_UHD, H_UHD = 3840, 2160
+PAYLOAD = 30720
+METRIC = "embed+extract megapixels/sec (4K RGB batch)"
+UNIT = "MP/s"
+PARAMS = dict(alpha=0.5, center=False, magmin=0.01, rmin=0.05, rmax=0.45)
+
+
+# ------------------------------------------------------------------------------------------------
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_frame_bits(n: int, payload: int, seed: int) -> np.ndarray:
+    """[n, 912 + 56*(payload+16)] bits with the reference's framing structure (Rep-3 header, Rep-7 payload)."""
+    rng = np.random.default_rng(seed)
+    raw = rng.integers(0, 2, size=(n, 304 + 8 * (payload + 16)), dtype=np.uint8)
+    return np.concatenate([np.repeat(raw[:, :304], 3, axis=1), np.repeat(raw[:, 304:], 7, axis=1)], axis=1)
+
+
+def make_covers(batch: int, W: int, H: int, distinct: int = 8) -> np.ndarray:
+    from steganosaurus_b200 import synth
+    base = [synth.gen_cover(W, H, 1000 + i) for i in range(min(distinct, batch))]
+    return np.stack([base[i % len(base)] for i in range(batch)])
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own hot-path functions (oracle/_ref) or the C port, one image
+# per worker process, all host cores.
+_CPU_STATE = None
+
+
+def _cpu_init(W, H, payload, use_ref):
+    """Pool initializer: every worker process builds its own image, bin list and frame once."""
+    global _CPU_STATE
+    sys.path.insert(0, ROOT)
+    from oracle import pyoracle as O
+    from steganosaurus_b200 import synth
+    idx = os.getpid() % 64
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    nbits = synth.frame_len(payload)
+    cover = synth.gen_cover(W, H, 1000 + idx)
+    bins = synth.random_bins(PH, PW, nbits, 21)
+    bits = make_frame_bits(1, payload, 2000 + idx)[0]
+    _CPU_STATE = (O.ref() if use_ref else O.port(), cover, bins, bits)
+
+
+def _cpu_ready(_):
+    time.sleep(0.2)
+    return _CPU_STATE is not None
+
+
+def _cpu_step(_):
+    o, cover, bins, bits = _CPU_STATE
+    t0 = time.time()
+    if o.kind == "reference":
+        te, stego = o.time_embed(cover, bins, bits, PARAMS["alpha"], PARAMS["center"], PARAMS["magmin"], PARAMS["rmin"], PARAMS["rmax"])
+        tx, _ = o.time_extract(stego, bins, PARAMS["alpha"], PARAMS["center"])
+    else:
+        e = o.embed(cover, bins, bits, PARAMS["alpha"], PARAMS["center"], PARAMS["magmin"], PARAMS["rmin"], PARAMS["rmax"])
+        o.extract(e["stego"], bins[:912], 3, PARAMS["alpha"], PARAMS["center"])
+        te = tx = 0.0
+    return t0, time.time(), te, tx
+
+
+class CpuArm:
+    def __init__(self, W, H, payload, workers=None):
+        import multiprocessing as mp
+        from oracle import pyoracle as O
+        self.use_ref = O.have_ref()
+        self.kind = "reference" if self.use_ref else "port"
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        try:
+            avail = int(open("/proc/meminfo").read().split("MemAvailable:")[1].split()[0]) * 1024
+        except Exception:
+            avail = 32 << 30
+        PH, PW = 1 << (H - 1).bit_length(), 1 << (W - 1).bit_length()
+        per = 140 * PH * PW  # reference needs ~130 B per padded bin
+        self.workers = max(1, min(ncpu, int(avail * 0.7 // per))) if workers is None else workers
+        self.W, self.H, self.payload = W, H, payload
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init, initargs=(W, H, payload, self.use_ref))
+        self.pool.map(_cpu_ready, range(self.workers), chunksize=1)  # wait until every worker is initialised
+
+    def step(self):
+        """All workers run one embed+extract of their own image concurrently; returns wall seconds."""
+        r = self.pool.map(_cpu_step, range(self.workers), chunksize=1)
+        return max(x[1] for x in r) - min(x[0] for x in r)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def describe(self, value):
+        return {"value": value, "unit": UNIT, "cores": self.workers, "kind": self.kind,
+                "sample": f"{self.workers} concurrent single-threaded processes x 1 image {self.W}x{self.H} "
+                          f"({self.payload}-byte frame) embed+extract per step; hot-path stages only "
+                          f"(to_planes..from_planes incl. median, capacity, F3 copy; PNG, KDF, walk excluded)"}
+
+
+def run_reference_arm(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return 0
+    arm = CpuArm(args.width, args.height, args.payload)
+    for _ in range(args.warmup):
+        arm.step()
+    ts = [arm.step() for _ in range(args.steps)]
+    arm.close()
+    t = float(np.mean(ts))
+    mp_per_step = arm.workers * args.width * args.height / 1e6
+    value = mp_per_step / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batch of 4K UHD RGB covers {args.width}x{args.height}, {args.payload}-byte frame "
+                               f"({912 + 56 * (args.payload + 16)} bits), embed+extract; CPU step = {arm.workers} images",
+                   "images_per_step": arm.workers},
+        "cpu_baseline": arm.describe(value),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import steganosaurus_b200 as sb
+    from steganosaurus_b200 import synth
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if args.gpus > 1 and world == 1:
+        print("bench.py: --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    W, H, B = args.width, args.height, args.batch
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    nbits = synth.frame_len(args.payload)
+    npay = args.payload + 16
+
+    # CPU baseline first (rank 0, N=1 only), before the GPU is busy
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(W, H, args.payload)
+        t = arm.step()
+        arm.close()
+        cpu_base = arm.describe(arm.workers * W * H / 1e6 / t)
+
+    # ---- synthetic workload (seeded)
+    bins_np = synth.random_bins(PH, PW, nbits, 21 + rank)
+    bits_np = make_frame_bits(B, args.payload, 2000 + rank)
+    covers_np = make_covers(B, W, H)
+    ctx = sb.Context(local_rank)
+
+    d_cover = torch.from_numpy(covers_np).to(dev)
+    d_bins = torch.from_numpy(bins_np.view(np.int32)).to(dev)
+    d_bits = torch.from_numpy(bits_np).to(dev)
+    d_stego = torch.empty_like(d_cover)
+    d_usable = torch.zeros(B, dtype=torch.int64, device=dev)
+    d_median = torch.zeros(B, 3, dtype=torch.float64, device=dev)
+    d_hdr = torch.zeros(B, 38, dtype=torch.uint8, device=dev)
+    d_pay = torch.zeros(B, npay, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        ctx.embed_batch_dev(d_cover, d_bins, d_bits, d_stego, usable=d_usable, median=d_median, **PARAMS)
+        ctx.extract_frame_dev(d_stego, d_bins, 912, d_hdr, d_pay, alpha=PARAMS["alpha"], center=PARAMS["center"])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg ("value")
+    for _ in range(args.warmup):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    barrier()
+    dev_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = ctx.launches - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    usable_min = int(d_usable.min().item())
+    changed = float((d_stego[0] != d_cover[0]).float().mean().item())
+
+    # ---- end-to-end leg: host buffers through the C-ABI, pinned memory, copies inside the timed region
+    del d_cover, d_stego, d_bits
+    torch.cuda.empty_cache()
+    h_cover = torch.from_numpy(covers_np).pin_memory()
+    h_bits = torch.from_numpy(bits_np).pin_memory()
+    h_stego = torch.empty_like(h_cover).pin_memory()
+    del covers_np, bits_np
+    hc, hb, hs = h_cover.numpy(), h_bits.numpy(), h_stego.numpy()
+
+    def step_e2e():
+        ctx.embed_batch(hc, bins_np, hb, out=hs, **PARAMS)
+        return ctx.extract_frame(hs, bins_np, 912, alpha=PARAMS["alpha"], center=PARAMS["center"])
+
+    e2e_steps = max(1, args.steps)
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        hdr, pay, _ = step_e2e()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_ms = max_over_ranks((t1 - t0) * 1e3) / e2e_steps
+    img_bytes = W * H * 3
+    h2d = B * (img_bytes + nbits) + B * img_bytes + 2 * 4 * nbits
+    d2h = B * img_bytes + B * 8 + B * (38 + npay)
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (max device time inside the timed region)
+    peak, peak_src = measured_peak_hbm()
+    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    name, (groups, ms, nbytes) = dom
+    ach = (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0
+    kernels = {k: {"groups": v[0], "ms": round(v[1], 3), "GBps": round((v[2] / 1e9) / (v[1] / 1e3), 1) if v[1] > 0 else None}
+               for k, v in prof.items() if v[0]}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("kernel") == name:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    mp_per_step = B * W * H / 1e6
+    line = {
+        "metric": METRIC, "value": world * mp_per_step / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"batch of {B} 4K UHD RGB covers {W}x{H} (pad {PW}x{PH}) per GPU, {args.payload}-byte frame "
+                               f"({nbits} bits, one shared bin list), embed+extract", "images_per_gpu_per_step": B,
+                   "l2": f"inputs larger than L2 ({B * img_bytes / 1e9:.1f} GB covers + {3 * PW * PH * 16 / 1e9:.2f} GB spectra per image)",
+                   "fft_impl": os.environ.get("TFFT_FFT_IMPL", "default"), "usable_min_bits": usable_min,
+                   "stego_pixels_changed": round(changed, 4)},
+        "clocks": clocks,
+        "e2e": {"value": world * mp_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "launch_groups": groups, "avg_ms_per_group": ms / groups if groups else None,
+                     "algorithmic_bytes_per_group": nbytes / groups if groups else None, "kernels": kernels},
+        "cpu_baseline": cpu_base,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--width", type=int, default=W_UHD)
+    ap.add_argument("--height", type=int, default=H_UHD)
+    ap.add_argument("--payload", type=int, default=PAYLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("bench.py: note -- warmup < 3 breaks the timing rules; use only for profiling runs", file=sys.stderr)
+    return run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

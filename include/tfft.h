@@ -100,6 +100,19 @@ int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, i
                           double alpha, int center, uint8_t* d_out_bytes, uint8_t* d_raw_bits,
                           void* stream);
 
+/* Whole-frame extract when the payload length is known (or bounded): ONE forward FFT per image,
+ * then the first nhdr_bins bins are voted rep-3 into out_hdr [n][ceil(nhdr_bins/3/8)] (the 38-byte
+ * header is nhdr_bins = 912, S:1223-1230) and the remaining bins rep-7 into out_payload
+ * [n][ceil((nbins-nhdr_bins)/7/8)] (S:1260-1268).  raw_bits [n][nbins] optional. */
+int tfft_extract_frame(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
+                       const uint32_t* bins, size_t nbins, size_t nhdr_bins, const double* jitter,
+                       double alpha, int center, uint8_t* out_hdr, uint8_t* out_payload,
+                       uint8_t* raw_bits);
+int tfft_extract_frame_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
+                           const uint32_t* d_bins, size_t nbins, size_t nhdr_bins,
+                           const double* d_jitter, double alpha, int center, uint8_t* d_out_hdr,
+                           uint8_t* d_out_payload, uint8_t* d_raw_bits, void* stream);
+
 /* Two-phase extract for the data dependency at S:1253 (payload length is only known after the
  * header has been decoded): tfft_forward_batch keeps the spectra of the batch resident in the
  * context; tfft_read_bits may then be called any number of times (header: 912 bins rep 3,
@@ -123,6 +136,28 @@ int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data_c64, int n, int PH, int PW, 
 int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec_c64, int n, int PH, int PW,
                              double magmin, double rmin, double rmax, double* d_median,
                              uint64_t* d_usable, void* stream);
+
+
+/* ---- per-kernel timing (CUDA events on the launching stream) -------------------------------
+ * When enabled, every kernel group the library launches is bracketed by a pair of events; after
+ * the caller has synchronised, tfft_profile_read() returns launches and summed device time per
+ * kind.  bench.py uses this for the roofline of the dominant kernel inside the timed region. */
+enum {
+    TFFT_K_ROW_FWD = 0,  /* row FFT, u8 -> c64 (fused plane split / centre / zero pad) */
+    TFFT_K_COL_FWD = 1,  /* column FFT c64 -> c64 */
+    TFFT_K_MEDIAN = 2,   /* median |F| + capacity count */
+    TFFT_K_EMBED = 3,    /* phase scatter */
+    TFFT_K_COL_INV = 4,  /* column IFFT */
+    TFFT_K_ROW_INV = 5,  /* row IFFT + scale/round/clamp/interleave/crop epilogue */
+    TFFT_K_EXTRACT = 6,  /* phase gather + vote + pack */
+    TFFT_K_C2C = 7,      /* plain c64 pass from the fft2d / fft_pass hooks */
+    TFFT_K_COUNT = 8
+};
+int tfft_profile_enable(tfft_ctx* ctx, int on);
+int tfft_profile_reset(tfft_ctx* ctx);
+/* total_bytes = algorithmic bytes the implemented groups must move (DESIGN.md lists the formulas) */
+int tfft_profile_read(tfft_ctx* ctx, int kind, uint64_t* groups, double* total_ms, double* total_bytes);
+const char* tfft_kind_name(int kind);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,8 @@ SYMBOLS = [
     "tfft_set_workspace_limit", "tfft_host_alloc", "tfft_host_free", "tfft_launch_count",
     "tfft_embed_batch", "tfft_embed_batch_dev", "tfft_extract_bits", "tfft_extract_bits_dev",
     "tfft_forward_batch", "tfft_read_bits", "tfft_forward_spectrum", "tfft_fft2d", "tfft_fft2d_dev",
-    "tfft_fft_pass_dev", "tfft_median_capacity_dev",
+    "tfft_fft_pass_dev", "tfft_median_capacity_dev", "tfft_extract_frame", "tfft_extract_frame_dev",
+    "tfft_profile_enable", "tfft_profile_reset", "tfft_profile_read", "tfft_kind_name",
 ]
 
 _lib = None
@@ -64,6 +65,19 @@ def load() -> C.CDLL:
     L.tfft_extract_bits.restype = i
     L.tfft_extract_bits_dev.argtypes = ext + [vp]
     L.tfft_extract_bits_dev.restype = i
+    frm = [vp, vp, i, i, i, vp, sz, sz, vp, d, i, vp, vp, vp]
+    L.tfft_extract_frame.argtypes = frm
+    L.tfft_extract_frame.restype = i
+    L.tfft_extract_frame_dev.argtypes = frm + [vp]
+    L.tfft_extract_frame_dev.restype = i
+    L.tfft_profile_enable.argtypes = [vp, i]
+    L.tfft_profile_enable.restype = i
+    L.tfft_profile_reset.argtypes = [vp]
+    L.tfft_profile_reset.restype = i
+    L.tfft_profile_read.argtypes = [vp, i, C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tfft_profile_read.restype = i
+    L.tfft_kind_name.argtypes = [i]
+    L.tfft_kind_name.restype = C.c_char_p
     L.tfft_forward_batch.argtypes = [vp, vp, i, i, i, i]
     L.tfft_forward_batch.restype = i
     L.tfft_read_bits.argtypes = [vp, vp, sz, i, vp, d, vp, vp]

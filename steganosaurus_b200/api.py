@@ -135,6 +135,20 @@ class Context:
                                              _ptr(raw) if (want_raw and bins.size) else None))
         return out, raw
 
+    def extract_frame(self, stego, bins, nhdr_bins=912, alpha=0.5, center=False, jitter=None, want_raw=False):
+        """One forward FFT per image; header bins voted rep-3, the rest rep-7 -> (hdr bytes, payload bytes, raw|None)."""
+        stego = np.ascontiguousarray(stego, np.uint8)
+        n, H, W, _ = stego.shape
+        bins = np.ascontiguousarray(bins, np.uint32)
+        jit = None if jitter is None else np.ascontiguousarray(jitter, np.float64)
+        nb, nbp = (nhdr_bins // 3 + 7) // 8, ((bins.size - nhdr_bins) // 7 + 7) // 8
+        hdr = np.zeros((n, nb), np.uint8)
+        pay = np.zeros((n, nbp), np.uint8)
+        raw = np.zeros((n, bins.size), np.uint8) if want_raw else None
+        self._check(self.L.tfft_extract_frame(self.h, _ptr(stego), n, W, H, _ptr(bins), bins.size, nhdr_bins, _ptr(jit),
+                                              alpha, int(center), _ptr(hdr), _ptr(pay) if nbp else None, _ptr(raw)))
+        return hdr, pay, raw
+
     def forward_batch(self, img, center=False):
         img = np.ascontiguousarray(img, np.uint8)
         n, H, W, _ = img.shape
@@ -187,6 +201,31 @@ class Context:
         self._check(self.L.tfft_extract_bits_dev(self.h, _dptr(stego), n, W, H, _dptr(bins), bins.numel(), rep,
                                                  _dptr(jitter), alpha, int(center), _dptr(out_bytes), _dptr(raw_bits),
                                                  self._stream()))
+
+    def extract_frame_dev(self, stego, bins, nhdr_bins, out_hdr, out_payload, raw_bits=None, alpha=0.5, center=False,
+                          jitter=None):
+        n, H, W, _ = stego.shape
+        self._check(self.L.tfft_extract_frame_dev(self.h, _dptr(stego), n, W, H, _dptr(bins), bins.numel(), nhdr_bins,
+                                                  _dptr(jitter), alpha, int(center), _dptr(out_hdr), _dptr(out_payload),
+                                                  _dptr(raw_bits), self._stream()))
+
+    # ------------------------------------------------------------------ per-kernel timing
+    KINDS = ["row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter", "col_inv", "row_inv_u8", "extract_vote", "c2c_pass"]
+
+    def profile_enable(self, on=True):
+        self._check(self.L.tfft_profile_enable(self.h, int(on)))
+
+    def profile_reset(self):
+        self._check(self.L.tfft_profile_reset(self.h))
+
+    def profile_read(self):
+        """{kind: (groups, total_ms, algorithmic_bytes)} -- call after synchronising the streams used."""
+        out = {}
+        for k, name in enumerate(self.KINDS):
+            g, ms, by = C.c_uint64(), C.c_double(), C.c_double()
+            self._check(self.L.tfft_profile_read(self.h, k, C.byref(g), C.byref(ms), C.byref(by)))
+            out[name] = (int(g.value), float(ms.value), float(by.value))
+        return out
 
     def fft2d_dev(self, data, inverse=False):
         """complex128 CUDA tensor [n,PH,PW], in place."""

@@ -44,6 +44,14 @@ struct tfft_ctx {
     // resident spectra for the two-phase extract
     int res_n = 0, res_PH = 0, res_PW = 0;
     char cuda_err[256] = {0};
+    // per-kernel-kind timing (tfft_profile_*)
+    bool prof_on = false;
+    struct ProfEvt { cudaEvent_t a, b; int kind; double bytes; };
+    std::vector<ProfEvt> prof_pending;
+    std::vector<cudaEvent_t> prof_pool;
+    double prof_ms[TFFT_K_COUNT] = {0};
+    double prof_bytes[TFFT_K_COUNT] = {0};
+    uint64_t prof_groups[TFFT_K_COUNT] = {0};
 };
 
 namespace {
@@ -108,6 +116,36 @@ Launcher make_launcher(tfft_ctx* ctx, cudaStream_t s) {
     return L;
 }
 
+// Brackets one kernel group with events on its stream when profiling is enabled.
+struct ProfScope {
+    tfft_ctx* c; cudaStream_t s; tfft_ctx::ProfEvt e; bool on;
+    static cudaEvent_t get(tfft_ctx* c) {
+        if (!c->prof_pool.empty()) { cudaEvent_t ev = c->prof_pool.back(); c->prof_pool.pop_back(); return ev; }
+        cudaEvent_t ev = nullptr;
+        cudaEventCreate(&ev);
+        return ev;
+    }
+    ProfScope(tfft_ctx* c_, cudaStream_t s_, int kind, double bytes) : c(c_), s(s_), on(c_->prof_on) {
+        if (!on) return;
+        e.kind = kind; e.bytes = bytes; e.a = get(c); e.b = get(c);
+        cudaEventRecord(e.a, s);
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(e.b, s);
+        c->prof_pending.push_back(e);
+    }
+};
+void prof_drain(tfft_ctx* c) {
+    for (auto& e : c->prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(e.b);
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->prof_ms[e.kind] += ms; c->prof_groups[e.kind]++; c->prof_bytes[e.kind] += e.bytes; }
+        c->prof_pool.push_back(e.a); c->prof_pool.push_back(e.b);
+    }
+    c->prof_pending.clear();
+}
+
 // images per chunk so that `nslots` spectrum workspaces fit the limit
 int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
     const size_t per_img = 3 * g.P * sizeof(double2);
@@ -160,11 +198,11 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
     a.img_in = d_img;
     a.axis = 0; a.log2n = g.lw; a.inverse = 0;
     a.in_rows = g.H;  // rows >= H are zero padding (S:395)
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_fft_pass(L, a)); }
     a.img_in = nullptr;
     a.in_rows = g.PH;
     a.axis = 1; a.log2n = g.lh;
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -173,11 +211,11 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
 int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
     a.axis = 0; a.log2n = g.lw;
     a.img_out = d_img;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403)
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -191,18 +229,28 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
     const int m = std::min(g.PH, g.PW);
-    CK(launch_median_capacity(L, spec, nimg * 3, g.PH, g.PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
-    CK(launch_embed(L, spec, nimg, g.PH, g.PW, d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable));
+    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.P);
+      CK(launch_median_capacity(L, spec, nimg * 3, g.PH, g.PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + 32.0 + 5.0));
+      CK(launch_embed(L, spec, nimg, g.PH, g.PW, d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
     return inverse_images(ctx, L, spec, d_stego, nimg, g, center);
 }
 
+// nhdr == 0: one segment of `rep`; nhdr > 0: rep-3 header segment + rep-7 payload segment (S:1223-1268)
 int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_stego, int nimg, const Geom& g,
-                  const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter, double alpha, int center,
-                  uint8_t* d_out_bytes, uint8_t* d_raw) {
+                  const uint32_t* d_bins, size_t nbins, int rep, size_t nhdr, const double* d_jitter, double alpha, int center,
+                  uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw) {
     double2* spec = (double2*)S.spec.p;
     int rc = forward_images(ctx, L, spec, d_stego, nimg, g, center);
     if (rc) return rc;
-    CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw));
+    ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
+    if (nhdr == 0) {
+        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+    } else {
+        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
+                          d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins));
+    }
     return TFFT_OK;
 }
 
@@ -295,8 +343,35 @@ void tfft_destroy(tfft_ctx* ctx) {
         if (S.stream) cudaStreamDestroy(S.stream);
     }
     release(ctx->bins); release(ctx->jitter);
+    prof_drain(ctx);
+    for (cudaEvent_t ev : ctx->prof_pool) cudaEventDestroy(ev);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
     delete ctx;
+}
+
+int tfft_profile_enable(tfft_ctx* ctx, int on) {
+    if (!ctx) return TFFT_E_INVALID;
+    ctx->prof_on = on != 0;
+    return TFFT_OK;
+}
+int tfft_profile_reset(tfft_ctx* ctx) {
+    if (!ctx) return TFFT_E_INVALID;
+    prof_drain(ctx);
+    for (int k = 0; k < TFFT_K_COUNT; k++) { ctx->prof_ms[k] = 0; ctx->prof_groups[k] = 0; ctx->prof_bytes[k] = 0; }
+    return TFFT_OK;
+}
+int tfft_profile_read(tfft_ctx* ctx, int kind, uint64_t* groups, double* total_ms, double* total_bytes) {
+    if (!ctx || kind < 0 || kind >= TFFT_K_COUNT) return TFFT_E_INVALID;
+    prof_drain(ctx);
+    if (groups) *groups = ctx->prof_groups[kind];
+    if (total_ms) *total_ms = ctx->prof_ms[kind];
+    if (total_bytes) *total_bytes = ctx->prof_bytes[kind];
+    return TFFT_OK;
+}
+const char* tfft_kind_name(int kind) {
+    static const char* names[TFFT_K_COUNT] = {"row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter",
+                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass"};
+    return (kind >= 0 && kind < TFFT_K_COUNT) ? names[kind] : "?";
 }
 
 int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes) {
@@ -393,10 +468,10 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
 }
 
 // ---------------------------------------------------------------------------------------------
-int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
-                          const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter,
-                          double alpha, int center, uint8_t* d_out_bytes, uint8_t* d_raw_bits, void* stream) {
-    if (!ctx || !d_stego || n < 0 || (nbins && !d_bins) || !(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+static int extract_dev_impl(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H, const uint32_t* d_bins, size_t nbins,
+                            int rep, size_t nhdr, const double* d_jitter, double alpha, int center, uint8_t* d_out,
+                            uint8_t* d_out_payload, uint8_t* d_raw_bits, void* stream) {
+    if (!ctx || !d_stego || n < 0 || (nbins && !d_bins) || nhdr > nbins) return TFFT_E_INVALID;
     Geom g;
     int rc = make_geom(W, H, g);
     if (rc) return rc;
@@ -407,21 +482,23 @@ int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, i
     Slot& S = ctx->slot[0];
     if ((rc = ensure_slot(ctx, S, g, chunk, false, 0, 0, 0))) return rc;
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
-    const size_t nb = dec_bytes(nbins, rep);
+    const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
+    const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);
-        rc = extract_chunk(ctx, L, S, d_stego + (size_t)i0 * g.img_bytes, m, g, d_bins, nbins, rep, d_jitter, alpha, center,
-                           d_out_bytes ? d_out_bytes + (size_t)i0 * nb : nullptr,
+        rc = extract_chunk(ctx, L, S, d_stego + (size_t)i0 * g.img_bytes, m, g, d_bins, nbins, rep, nhdr, d_jitter, alpha, center,
+                           d_out ? d_out + (size_t)i0 * nb : nullptr,
+                           d_out_payload ? d_out_payload + (size_t)i0 * nbp : nullptr,
                            d_raw_bits ? d_raw_bits + (size_t)i0 * nbins : nullptr);
         if (rc) return rc;
     }
     return TFFT_OK;
 }
 
-int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
-                      const uint32_t* bins, size_t nbins, int rep, const double* jitter,
-                      double alpha, int center, uint8_t* out_bytes, uint8_t* raw_bits) {
-    if (!ctx || !stego || n < 0 || (nbins && !bins) || !(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H, const uint32_t* bins, size_t nbins,
+                             int rep, size_t nhdr, const double* jitter, double alpha, int center, uint8_t* out,
+                             uint8_t* out_payload, uint8_t* raw_bits) {
+    if (!ctx || !stego || n < 0 || (nbins && !bins) || nhdr > nbins) return TFFT_E_INVALID;
     Geom g;
     int rc = make_geom(W, H, g);
     if (rc) return rc;
@@ -431,9 +508,11 @@ int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
     ctx->res_n = 0;
     const int chunk = chunk_for(ctx, g, n, 2);
     const int nslots = (n > chunk) ? 2 : 1;
-    const size_t nb = dec_bytes(nbins, rep);
+    const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
+    const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
+    // header bytes and payload bytes share one device buffer per slot: [chunk][nb] then [chunk][nbp]
     for (int s = 0; s < nslots; s++)
-        if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, 0, out_bytes ? nb : 0, raw_bits ? nbins : 0))) return rc;
+        if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, 0, (out ? nb : 0) + (out_payload ? nbp : 0), raw_bits ? nbins : 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbins, jitter, ctx->slot[0].stream))) return rc;
     int ci = 0;
     for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
@@ -442,15 +521,44 @@ int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
         cudaStream_t st = S.stream;
         CK(cudaMemcpyAsync(S.in.p, stego + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
         Launcher L = make_launcher(ctx, st);
-        rc = extract_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, nbins, rep,
-                           jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center,
-                           out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr);
+        uint8_t* d_out = out ? (uint8_t*)S.outbytes.p : nullptr;
+        uint8_t* d_pay = out_payload ? (uint8_t*)S.outbytes.p + (out ? (size_t)chunk * nb : 0) : nullptr;
+        rc = extract_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, nbins, rep, nhdr,
+                           jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, d_out, d_pay,
+                           raw_bits ? (uint8_t*)S.raw.p : nullptr);
         if (rc) return rc;
-        if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes + (size_t)i0 * nb, S.outbytes.p, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
+        if (d_out && nb) CK(cudaMemcpyAsync(out + (size_t)i0 * nb, d_out, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
+        if (d_pay && nbp) CK(cudaMemcpyAsync(out_payload + (size_t)i0 * nbp, d_pay, (size_t)m * nbp, cudaMemcpyDeviceToHost, st));
         if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits + (size_t)i0 * nbins, S.raw.p, (size_t)m * nbins, cudaMemcpyDeviceToHost, st));
     }
     for (int s = 0; s < nslots; s++) CK(cudaStreamSynchronize(ctx->slot[s].stream));
     return TFFT_OK;
+}
+
+int tfft_extract_bits_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
+                          const uint32_t* d_bins, size_t nbins, int rep, const double* d_jitter,
+                          double alpha, int center, uint8_t* d_out_bytes, uint8_t* d_raw_bits, void* stream) {
+    if (!(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+    return extract_dev_impl(ctx, d_stego, n, W, H, d_bins, nbins, rep, 0, d_jitter, alpha, center, d_out_bytes, nullptr, d_raw_bits, stream);
+}
+int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
+                      const uint32_t* bins, size_t nbins, int rep, const double* jitter,
+                      double alpha, int center, uint8_t* out_bytes, uint8_t* raw_bits) {
+    if (!(rep == 1 || rep == 3 || rep == 7)) return TFFT_E_INVALID;
+    return extract_host_impl(ctx, stego, n, W, H, bins, nbins, rep, 0, jitter, alpha, center, out_bytes, nullptr, raw_bits);
+}
+int tfft_extract_frame_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, int H,
+                           const uint32_t* d_bins, size_t nbins, size_t nhdr_bins, const double* d_jitter,
+                           double alpha, int center, uint8_t* d_out_hdr, uint8_t* d_out_payload,
+                           uint8_t* d_raw_bits, void* stream) {
+    if (nhdr_bins == 0) return TFFT_E_INVALID;
+    return extract_dev_impl(ctx, d_stego, n, W, H, d_bins, nbins, 3, nhdr_bins, d_jitter, alpha, center, d_out_hdr, d_out_payload, d_raw_bits, stream);
+}
+int tfft_extract_frame(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
+                       const uint32_t* bins, size_t nbins, size_t nhdr_bins, const double* jitter,
+                       double alpha, int center, uint8_t* out_hdr, uint8_t* out_payload, uint8_t* raw_bits) {
+    if (nhdr_bins == 0) return TFFT_E_INVALID;
+    return extract_host_impl(ctx, stego, n, W, H, bins, nbins, 3, nhdr_bins, jitter, alpha, center, out_hdr, out_payload, raw_bits);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,6 +595,7 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
     if (raw_bits && nbins && (rc = ensure(ctx, S.raw, (size_t)n * nbins))) return rc;
     if ((rc = upload_bins(ctx, bins, nbins, jitter, S.stream))) return rc;
     Launcher L = make_launcher(ctx, S.stream);
+    ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (16.0 + 4.0));
     CK(launch_extract(L, (const double2*)S.spec.p, n, ctx->res_PH, ctx->res_PW, (const uint32_t*)ctx->bins.p, nbins, rep,
                       jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
                       out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr));
@@ -513,9 +622,9 @@ static int fft2d_planes(tfft_ctx* ctx, const Launcher& L, double2* d, int nplane
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
     a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
     a.axis = 0; a.log2n = ilog2(PW);  // rows, then columns (S:361-365)
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)a.nplanes * 32.0 * (double)PH * PW); CK(launch_fft_pass(L, a)); }
     a.axis = 1; a.log2n = ilog2(PH);
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)a.nplanes * 32.0 * (double)PH * PW); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 static int check_dims(int PH, int PW) {
@@ -546,7 +655,7 @@ int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data, int n, int PH, int PW, int 
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
     a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
     a.axis = axis; a.log2n = ilog2(axis == 0 ? PW : PH);
-    CK(launch_fft_pass(L, a));
+    { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)a.nplanes * 32.0 * (double)PH * PW); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -586,6 +695,7 @@ int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec, int n, int PH,
     median_work_carve(mw, S.med.p, n * 3, CAND_CAP);
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
     const int m = std::min(PH, PW);
+    ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)n * 3.0 * 16.0 * (double)PH * PW);
     CK(launch_median_capacity(L, (const double2*)d_spec, n * 3, PH, PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
     return TFFT_OK;
 }

@@ -488,11 +488,11 @@ __device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, in
 
 __global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ spec, size_t P, const uint32_t* __restrict__ bins,
                                                    size_t nbins, const double* __restrict__ jitter, double alpha,
-                                                   uint8_t* raw_bits) {
+                                                   uint8_t* raw_bits, size_t raw_stride) {
     const int img = blockIdx.y;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbins) return;
-    raw_bits[(size_t)img * nbins + i] = (uint8_t)read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
+    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
 }
 
 // one thread per decoded bit; a warp packs 32 decoded bits into 4 bytes with a ballot
@@ -518,11 +518,11 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
 
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
-                           uint8_t* out_bytes, uint8_t* raw_bits) {
+                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride) {
     if (nimg == 0) return cudaSuccess;
     const size_t P = (size_t)PH * PW;
     if (raw_bits && nbins) {
-        extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits);
+        extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits, raw_stride ? raw_stride : nbins);
         TFFT_LAUNCH_CHECK(L);
     }
     const size_t ndec = nbins / (size_t)rep;

@@ -69,6 +69,6 @@ cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, int PH, int
 // ---- extract gather + vote (read_bit_from_bin S:734-746, rep3/7 S:468/S:501, pack S:447) --
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
-                           uint8_t* out_bytes, uint8_t* raw_bits);
+                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
 
 }  // namespace tfft

@@ -142,6 +142,16 @@ def test_two_phase_extract(ctx):
     assert np.array_equal(np.concatenate([raw3[0], raw7[0]]), g["raw_all"][: 912 + rest.size // 7 * 7])
 
 
+def test_extract_frame(ctx):
+    """Header (rep 3) + payload (rep 7) in one call == the two separate reads."""
+    g = load_golden("g512_walk")
+    nb = g["bins"].size
+    nb = 912 + (nb - 912) // 7 * 7
+    hdr, pay, raw = ctx.extract_frame(g["stego"][None], g["bins"][:nb], 912, g["alpha"], g["center"], want_raw=True)
+    assert np.array_equal(hdr[0], g["dec3"]) and np.array_equal(pay[0], g["dec7"])
+    assert np.array_equal(raw[0], g["raw_all"][:nb])
+
+
 def test_capacity_error_and_passthrough(ctx):
     """S:1009-1012: nbits > usable -> error with the same counts; the image passes through unmodified."""
     cover = synth.gen_cover(256, 256, 5)
@@ -243,8 +253,15 @@ def test_full_size_roundtrip_properties(ctx):
     bits1 = synth.random_bits(1, 304 + 8 * (30720 + 16), 22)[0]
     bits = np.concatenate([np.repeat(bits1[:304], 3), np.repeat(bits1[304:], 7)])[None]
     stego, usable, med = ctx.embed_batch(cover[None], bins, bits)
-    assert int(usable[0]) == 3950328  # SURVEY section 6.2, last row
-    assert abs(med[0, 0] - 19664.9) / 19664.9 < 0.05
+    # integer parity at full size: capacity count and medians against the oracle port's own
+    # forward spectrum (SURVEY section 6.2 quotes ~3.95 M usable bits / median ~19 665 for this kind of cover)
+    o = O.port()
+    F = o.forward_spectrum(cover)
+    wmed = [o.median_abs(F[p]) for p in range(3)]
+    wus = sum(o.count_plane(F[p], 0.05, 0.45, 0.01 * wmed[p]) for p in range(3))
+    assert int(usable[0]) == wus and 3.9e6 < wus < 4.0e6
+    assert np.allclose(med[0], wmed, rtol=1e-11) and abs(med[0, 0] - 19664.9) / 19664.9 < 0.05
+    del F
     d3, raw3 = ctx.extract_bits(stego, bins[:912], 3)
     d7, raw7 = ctx.extract_bits(stego, bins[912:], 7)
     assert np.array_equal(d3[0], np.packbits(bits1[:304]))
