@@ -198,11 +198,10 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
     a.img_in = d_img;
     a.axis = 0; a.log2n = g.lw; a.inverse = 0;
     a.in_rows = g.H;  // rows >= H are zero padding (S:395)
-    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_fft_pass(L, a)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
     a.img_in = nullptr;
-    a.in_rows = g.PH;
-    a.axis = 1; a.log2n = g.lh;
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+    a.axis = 1; a.log2n = g.lh;  // in_rows stays H: the row pass left rows >= H unwritten (they are zero)
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * g.PW + (double)g.P)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -211,7 +210,8 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
 int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+    a.out_rows = g.H;  // rows >= H are cropped away (S:399-403): the column pass does not store them
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.P + (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
     a.axis = 0; a.log2n = g.lw;
     a.img_out = d_img;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403)

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(512) fft_pass_v0(PassArgs a, int cpc) {
             const int y = o0 + c;
             v = (y < a.in_rows) ? plane[(size_t)y * a.PW + k] : make_double2(0.0, 0.0);
         } else {
-            v = plane[(size_t)k * a.PW + o0 + c];
+            v = (k < a.in_rows) ? plane[(size_t)k * a.PW + o0 + c] : make_double2(0.0, 0.0);
         }
         sm[c * n + (int)(__brev((unsigned)k) >> (32 - a.log2n))] = v;
     }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(512) fft_pass_v0(PassArgs a, int cpc) {
             }
         } else if (a.axis == 0) {
             plane[(size_t)(o0 + c) * a.PW + k] = v;
-        } else {
+        } else if (k < a.out_rows) {
             plane[(size_t)k * a.PW + o0 + c] = v;
         }
     }

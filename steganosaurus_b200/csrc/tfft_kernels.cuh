@@ -28,9 +28,10 @@ struct PassArgs {
     int axis;     // 0: along x (rows), 1: along y (columns)
     int inverse;  // 0: e^{+i} (reference forward), 1: e^{-i} and scale by 1/n (S:357)
     int center;   // apply_center S:392 on the image side of IN_U8 / OUT_U8
-    // Zero-structure hints (never change results, only skip work on known-zero data):
-    int in_rows;  // axis 0, IN_C64/IN_U8: rows y >= in_rows are known to be all-zero on input
-    int out_rows; // axis 0, OUT_*: rows y >= out_rows need not be produced
+    // Zero-structure hints in plane-row coordinates (never change results, only skip work):
+    int in_rows;  // plane rows y >= in_rows are all-zero on input and are NOT read
+                  //   (axis 0: such pencils are skipped; axis 1: those elements are zero-filled)
+    int out_rows; // plane rows y >= out_rows are not needed downstream and are NOT written
 };
 
 struct Launcher {

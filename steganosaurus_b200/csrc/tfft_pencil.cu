@@ -1,9 +1,541 @@
-// tfft_pencil.cu -- register/shared-memory "pencil" FFT passes (filled in after v0 is validated).
+// tfft_pencil.cu -- the fast FFT passes ("pencil" kernels) for N = 512 .. 4096.
+//
+// A pencil is one row or one column of a padded plane.  N = R1 * 16 * 16 with R1 = N/256 in
+// {2,4,8,16}: three Cooley-Tukey stages (decimation in frequency) whose butterflies live in
+// registers (16 complex doubles per thread); data moves between stages through shared memory:
+//
+//   global --cp.async 16B--> L (dense landing buffer, 16 B entries)
+//   stage 1 (radix R1, stride 256)  in place in L                       [1 barrier]
+//   stage 2 (radix 16, stride 16)   reads L, then L is free: the NEXT pencil's cp.async loads
+//                                   are issued here and overlap everything below
+//   exchange 2 through X (8 B entries, re then im, XOR-swizzled -> conflict-free)  [3 barriers]
+//   stage 3 (radix 16, stride 1)    results leave the registers straight to global memory
+//
+// A "unit" is the set of threads that owns one L/X pair and works through its own stream of
+// pencils (persistent, static round-robin); a CTA hosts several units that only synchronise
+// among themselves (named barriers), so one unit's shared-memory phase overlaps another's FP64
+// phase.  Column passes process VEC adjacent columns per unit with the column index on the
+// fastest lanes, so every global access is a full 32 B sector (VEC=2) or more.
+//
+// Fused variants: u8 RGB row -> three forward row pencils (plane split, centre sign, zero pad;
+// to_planes_u8 S:383, apply_center S:392, pad_to_fft S:393) and three inverse row pencils -> u8 RGB
+// row (scale, crop, centre, round, clamp, interleave; S:357, ifft_crop S:399, from_planes_u8 S:387).
+// Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
 #include "tfft_kernels.cuh"
 
 namespace tfft {
-cudaError_t launch_fft_pass_pencil(const Launcher&, const PassArgs&, bool* handled) {
-    *handled = false;
-    return cudaSuccess;
+namespace pk {
+
+// ------------------------------------------------------------------------------------------
+// complex helpers (double2 = re, im)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -a.y * b.y), fma(a.x, b.y, a.y * b.x));
 }
+// multiply by S*i
+template <int S>
+__device__ __forceinline__ double2 mul_si(double2 a) {
+    return S > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+// multiply by the constant (wr, S*wi)
+template <int S>
+__device__ __forceinline__ double2 cmulc(double2 a, double wr, double wi) {
+    const double si = S > 0 ? wi : -wi;
+    return make_double2(fma(a.x, wr, -a.y * si), fma(a.x, si, a.y * wr));
+}
+
+constexpr double C8 = 0.70710678118654752440;   // cos(pi/4)
+constexpr double C16 = 0.92387953251128673848;  // cos(pi/8)
+constexpr double S16 = 0.38268343236508978178;  // sin(pi/8)
+
+// X[k] = sum_n x[n] (S*i)^{nk}, in place, natural order
+template <int S>
+__device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, double2& a3) {
+    const double2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_si<S>(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+// In-register DFT of R points with w = exp(S*2*pi*i/R).  Output X[k] is left at x[oidx<R>(k)].
+template <int R>
+__device__ __host__ constexpr int oidx(int k) {
+    return R == 16 ? 4 * (k & 3) + (k >> 2) : R == 8 ? 2 * (k & 3) + (k >> 2) : k;
+}
+
+template <int S, int R>
+__device__ __forceinline__ void dft(double2* x) {
+    if constexpr (R == 2) {
+        const double2 a = x[0], b = x[1];
+        x[0] = cadd(a, b); x[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        dft4<S>(x[0], x[1], x[2], x[3]);
+    } else if constexpr (R == 8) {
+        // n = 2 n1 + n2, k = k1 + 4 k2
+        dft4<S>(x[0], x[2], x[4], x[6]);
+        dft4<S>(x[1], x[3], x[5], x[7]);  // y[n2][k1] at x[2 k1 + n2]
+        x[3] = cmulc<S>(x[3], C8, C8);    // w8^1
+        x[5] = mul_si<S>(x[5]);           // w8^2
+        x[7] = cmulc<S>(x[7], -C8, C8);   // w8^3
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) {
+            const double2 a = x[2 * k1], b = x[2 * k1 + 1];
+            x[2 * k1] = cadd(a, b); x[2 * k1 + 1] = csub(a, b);
+        }
+    } else {
+        static_assert(R == 16, "radix");
+        // n = 4 n1 + n2, k = k1 + 4 k2
+#pragma unroll
+        for (int n2 = 0; n2 < 4; n2++) dft4<S>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2]);  // y[n2][k1] at x[4 k1 + n2]
+        // twiddle w16^{n2 k1}
+        x[5] = cmulc<S>(x[5], C16, S16);    // 1
+        x[6] = cmulc<S>(x[6], C8, C8);      // 2
+        x[7] = cmulc<S>(x[7], S16, C16);    // 3
+        x[9] = cmulc<S>(x[9], C8, C8);      // 2
+        x[10] = mul_si<S>(x[10]);           // 4
+        x[11] = cmulc<S>(x[11], -C8, C8);   // 6
+        x[13] = cmulc<S>(x[13], S16, C16);  // 3
+        x[14] = cmulc<S>(x[14], -C8, C8);   // 6
+        x[15] = cmulc<S>(x[15], -C16, -S16);  // 9
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) dft4<S>(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);
+    }
+}
+
+// X[k] *= w1^k for k = 1..R-1 (outputs addressed through oidx)
+template <int R>
+__device__ __forceinline__ void twiddle(double2* x, double2 w1) {
+    double2 w = w1;
+#pragma unroll
+    for (int k = 1; k < R; k++) {
+        x[oidx<R>(k)] = cmul(x[oidx<R>(k)], w);
+        if (k + 1 < R) w = cmul(w, w1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// async copy + named barrier primitives
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void unit_bar(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint8_t clamp8(double v) {  // from_planes_u8 S:389
+    double r = round(v);
+    r = fmax(0.0, fmin(255.0, r));
+    return (uint8_t)r;
+}
+
+// ------------------------------------------------------------------------------------------
+// compile-time geometry of one unit
+// ------------------------------------------------------------------------------------------
+template <int LOG2N, int VEC>
+struct Geo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int R1 = N / 256;          // first-stage radix
+    static constexpr int TP = N / 16;           // threads per pencil
+    static constexpr int UT = TP * VEC;         // threads per unit
+    static constexpr int J1 = 16 / R1;          // stage-1 butterflies per thread
+    static constexpr size_t L_BYTES = (size_t)N * VEC * 16;
+    static constexpr size_t X_BYTES = (size_t)N * VEC * 8;
+};
+
+enum Mode { M_C2C_ROW = 0, M_C2C_COL = 1, M_U8_FWD = 2, M_U8_INV = 3 };
+
+// XOR swizzle of exchange-2 positions p = k1*256 + k2*16 + low4: low4 ^= (k1 + R1*k2) & 15
+template <int R1>
+__device__ __forceinline__ int swz(int k1, int k2, int low) { return (k1 << 8) | (k2 << 4) | (low ^ ((k1 + R1 * k2) & 15)); }
+
+// ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
+template <int S, int LOG2N, int VEC, bool FROM_U8>
+__device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
+                                       const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/) {
+    using G = Geo<LOG2N, VEC>;
+#pragma unroll
+    for (int j = 0; j < G::J1; j++) {
+        const int m = tt + j * G::TP;  // 0..255
+        double2 x[G::R1];
+#pragma unroll
+        for (int n = 0; n < G::R1; n++) {
+            if constexpr (FROM_U8) {
+                const int xc = n * 256 + m;
+                double v = 0.0;
+                if (xc < W) {
+                    v = (double)urow[xc * 3 + ch];
+                    if (negmask >= 0 && ((xc + negmask) & 1)) v = -v;  // apply_center S:392
+                }
+                x[n] = make_double2(v, 0.0);
+            } else {
+                x[n] = L[(n * 256 + m) * VEC + c];
+            }
+        }
+        dft<S, G::R1>(x);
+        double2 w1 = tw[(size_t)m << (TW_LOG2 - LOG2N)];
+        if (S < 0) w1.y = -w1.y;
+        twiddle<G::R1>(x, w1);
+#pragma unroll
+        for (int k = 0; k < G::R1; k++) L[(k * 256 + m) * VEC + c] = x[oidx<G::R1>(k)];
+    }
+}
+
+// ---- stage 2 load: radix 16, stride 16 -------------------------------------------------------
+template <int LOG2N, int VEC>
+__device__ __forceinline__ void stage2_load(const double2* L, int tt, int c, double2* x) {
+    const int k1 = tt >> 4, m = tt & 15;
+#pragma unroll
+    for (int n = 0; n < 16; n++) x[n] = L[(k1 * 256 + n * 16 + m) * VEC + c];
+}
+
+// ---- stage 2 compute + exchange 2 through X + stage 3 compute -------------------------------
+// on return x[oidx<16>(k3)] holds output element tt + TP*k3
+template <int S, int LOG2N, int VEC>
+__device__ __forceinline__ void stage23(double* X, int tt, int c, const double2* __restrict__ tw, double2* x,
+                                        int bar_id) {
+    using G = Geo<LOG2N, VEC>;
+    const int k1 = tt >> 4, m = tt & 15;
+    dft<S, 16>(x);
+    double2 w1 = tw[(size_t)m << (TW_LOG2 - 8)];
+    if (S < 0) w1.y = -w1.y;
+    twiddle<16>(x, w1);
+    // thread of stage 3: tt = k1' + R1*k2'
+    const int k1r = tt & (G::R1 - 1), k2r = tt / G::R1;
+    double2 z[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) X[swz<G::R1>(k1, k2, m) * VEC + c] = x[oidx<16>(k2)].x;
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int n = 0; n < 16; n++) z[n].x = X[swz<G::R1>(k1r, k2r, n) * VEC + c];
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) X[swz<G::R1>(k1, k2, m) * VEC + c] = x[oidx<16>(k2)].y;
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int n = 0; n < 16; n++) z[n].y = X[swz<G::R1>(k1r, k2r, n) * VEC + c];
+    dft<S, 16>(z);
+#pragma unroll
+    for (int n = 0; n < 16; n++) x[n] = z[n];
+}
+
+// ------------------------------------------------------------------------------------------
+// C2C pass (rows: VEC = 1, columns: VEC columns per unit)
+// ------------------------------------------------------------------------------------------
+struct C2CArgs {
+    double2* spec;
+    const double2* tw;
+    long long nitems;   // pencil groups: rows: nplanes*PH ; columns: nplanes*PW/VEC
+    int PW, PH;
+    int in_rows, out_rows;
+};
+
+template <int S, int LOG2N, int VEC, int MODE, int UNITS>
+__global__ void __launch_bounds__(Geo<LOG2N, VEC>::UT* UNITS, 1) pencil_c2c(C2CArgs a) {
+    using G = Geo<LOG2N, VEC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int unit = threadIdx.x / G::UT, ut = threadIdx.x % G::UT;
+    const int c = ut % VEC, tt = ut / VEC;
+    double2* L = (double2*)(smem_raw + (size_t)unit * (G::L_BYTES + G::X_BYTES));
+    double* X = (double*)((unsigned char*)L + G::L_BYTES);
+    const int bar_id = 1 + unit;
+    const long long stride = (long long)gridDim.x * UNITS;
+    long long item = (long long)blockIdx.x * UNITS + unit;
+    const double scale = S < 0 ? 1.0 / (double)G::N : 1.0;  // S:357
+
+    // element e = k*VEC + c of item -> global pointer; returns validity (zero rows are not read)
+    auto gptr = [&](long long it, int k, int cc, bool& valid) -> double2* {
+        if constexpr (MODE == M_C2C_ROW) {
+            const long long ip = it / a.PH;
+            const int y = (int)(it % a.PH);
+            valid = y < a.in_rows;
+            return a.spec + ((size_t)ip * a.PH + y) * a.PW + k;
+        } else {
+            const int gpp = a.PW / VEC;
+            const long long ip = it / gpp;
+            const int x0 = (int)(it % gpp) * VEC;
+            valid = k < a.in_rows;
+            return a.spec + ((size_t)ip * a.PH + k) * a.PW + x0 + cc;
+        }
+    };
+    auto issue_loads = [&](long long it) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int e = ut + i * G::UT;
+            bool valid;
+            double2* g = gptr(it, e / VEC, e % VEC, valid);
+            cp_async16(&L[e], valid ? (const void*)g : (const void*)a.spec, valid ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    if (item < a.nitems) issue_loads(item);
+    for (; item < a.nitems; item += stride) {
+        cp_async_wait_all();
+        unit_bar(bar_id, G::UT);
+        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1);
+        unit_bar(bar_id, G::UT);
+        double2 x[16];
+        stage2_load<LOG2N, VEC>(L, tt, c, x);
+        unit_bar(bar_id, G::UT);  // L is free
+        if (item + stride < a.nitems) issue_loads(item + stride);
+        stage23<S, LOG2N, VEC>(X, tt, c, a.tw, x, bar_id);
+#pragma unroll
+        for (int k3 = 0; k3 < 16; k3++) {
+            const int k = tt + G::TP * k3;
+            bool valid;
+            double2* g = gptr(item, k, c, valid);
+            double2 v = x[oidx<16>(k3)];
+            v.x *= scale; v.y *= scale;
+            if (MODE == M_C2C_ROW || k < a.out_rows) *g = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// u8 RGB row -> three forward row pencils.  item = (image, y < H)
+// ------------------------------------------------------------------------------------------
+struct U8Args {
+    double2* spec;
+    const double2* tw;
+    const uint8_t* img_in;
+    uint8_t* img_out;
+    long long nitems;  // nimg * H
+    int W, H, PW, PH, center;
+};
+
+template <int LOG2N>
+struct U8Geo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr size_t U_BYTES = (size_t)N * 3 + 32;  // aligned span of one RGB row (W <= N)
+};
+
+template <int LOG2N, int UNITS>
+__global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd(U8Args a) {
+    using G = Geo<LOG2N, 1>;
+    constexpr size_t UB = U8Geo<LOG2N>::U_BYTES;
+    constexpr size_t UNIT_BYTES = G::L_BYTES + 2 * UB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
+    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    double2* L = (double2*)base;
+    double* X = (double*)base;  // exchange 2 also runs inside L here (no landing to protect), 8 B view
+    unsigned char* U[2] = {base + G::L_BYTES, base + G::L_BYTES + UB};
+    const int bar_id = 1 + unit;
+    const long long stride = (long long)gridDim.x * UNITS;
+    long long item = (long long)blockIdx.x * UNITS + unit;
+    const size_t row_bytes = (size_t)a.W * 3;
+    const uintptr_t img_base = (uintptr_t)a.img_in;
+    const uintptr_t img_end = img_base + (size_t)(a.nitems)*row_bytes;
+
+    auto issue_row = [&](long long it, unsigned char* dst) {
+        const uintptr_t start = img_base + (size_t)it * row_bytes;
+        const uintptr_t a0 = start & ~(uintptr_t)15;
+        const int nchunks = (int)((start + row_bytes - a0 + 15) >> 4);
+        for (int i = tt; i < nchunks; i += G::UT) {
+            const uintptr_t src = a0 + (size_t)i * 16;
+            long long avail = (long long)(img_end - src);
+            int nb = avail >= 16 ? 16 : (avail > 0 ? (int)avail : 0);
+            cp_async16(dst + (size_t)i * 16, (const void*)(nb ? src : img_base), nb);
+        }
+        cp_async_commit();
+    };
+
+    int buf = 0;
+    if (item < a.nitems) issue_row(item, U[0]);
+    for (; item < a.nitems; item += stride, buf ^= 1) {
+        cp_async_wait_all();
+        unit_bar(bar_id, G::UT);
+        if (item + stride < a.nitems) issue_row(item + stride, U[buf ^ 1]);
+        const long long img = item / a.H;
+        const int y = (int)(item % a.H);
+        const uint8_t* urow = U[buf] + ((img_base + (size_t)item * row_bytes) & 15);
+        for (int ch = 0; ch < 3; ch++) {
+            stage1<+1, LOG2N, 1, true>(L, tt, 0, a.tw, urow, a.W, ch, a.center ? (y & 1) : -1);
+            unit_bar(bar_id, G::UT);
+            double2 x[16];
+            stage2_load<LOG2N, 1>(L, tt, 0, x);
+            unit_bar(bar_id, G::UT);
+            stage23<+1, LOG2N, 1>(X, tt, 0, a.tw, x, bar_id);
+            double2* out = a.spec + (((size_t)img * 3 + ch) * a.PH + y) * a.PW;
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) out[tt + G::TP * k3] = x[oidx<16>(k3)];
+            unit_bar(bar_id, G::UT);  // X (inside L) is rewritten by the next plane's stage 1
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// three inverse row pencils -> u8 RGB row.  item = (image, y < H)
+// ------------------------------------------------------------------------------------------
+template <int LOG2N, int UNITS>
+__global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv(U8Args a) {
+    using G = Geo<LOG2N, 1>;
+    constexpr size_t UB = U8Geo<LOG2N>::U_BYTES;
+    constexpr size_t UNIT_BYTES = G::L_BYTES + G::X_BYTES + UB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
+    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    double2* L = (double2*)base;
+    double* X = (double*)(base + G::L_BYTES);
+    unsigned char* O = base + G::L_BYTES + G::X_BYTES;
+    const int bar_id = 1 + unit;
+    const long long stride = (long long)gridDim.x * UNITS;
+    long long item = (long long)blockIdx.x * UNITS + unit;
+    const size_t row_bytes = (size_t)a.W * 3;
+    const double scale = 1.0 / (double)G::N;
+
+    auto src_row = [&](long long it, int ch) -> const double2* {
+        const long long img = it / a.H;
+        const int y = (int)(it % a.H);
+        return a.spec + (((size_t)img * 3 + ch) * a.PH + y) * a.PW;
+    };
+    auto issue_loads = [&](const double2* src) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int e = tt + i * G::UT;
+            cp_async16(&L[e], src + e, 16);
+        }
+        cp_async_commit();
+    };
+
+    if (item < a.nitems) issue_loads(src_row(item, 0));
+    for (; item < a.nitems; item += stride) {
+        const int y = (int)(item % a.H);
+        const uintptr_t gstart = (uintptr_t)a.img_out + (size_t)item * row_bytes;
+        const int off = (int)(gstart & 15);
+        for (int ch = 0; ch < 3; ch++) {
+            cp_async_wait_all();
+            unit_bar(bar_id, G::UT);
+            stage1<-1, LOG2N, 1, false>(L, tt, 0, a.tw, nullptr, 0, 0, -1);
+            unit_bar(bar_id, G::UT);
+            double2 x[16];
+            stage2_load<LOG2N, 1>(L, tt, 0, x);
+            unit_bar(bar_id, G::UT);  // L is free: prefetch the next plane / next item's first plane
+            if (ch < 2) issue_loads(src_row(item, ch + 1));
+            else if (item + stride < a.nitems) issue_loads(src_row(item + stride, 0));
+            stage23<-1, LOG2N, 1>(X, tt, 0, a.tw, x, bar_id);
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) {
+                const int k = tt + G::TP * k3;
+                if (k < a.W) {
+                    double v = x[oidx<16>(k3)].x * scale;           // ifft_crop S:401: real part
+                    if (a.center && ((k + y) & 1)) v = -v;           // S:1102
+                    O[off + k * 3 + ch] = clamp8(v);
+                }
+            }
+        }
+        unit_bar(bar_id, G::UT);
+        // O[off .. off+row_bytes) -> global; aligned 16 B chunks in the middle, bytes at the edges
+        {
+            unsigned char* gdst = (unsigned char*)(gstart - off);
+            const int total = off + (int)row_bytes;
+            const int nchunks = (total + 15) >> 4;
+            for (int i = tt; i < nchunks; i += G::UT) {
+                const int b0 = i * 16, b1 = b0 + 16;
+                if (b0 >= off && b1 <= total) {
+                    *(uint4*)(gdst + b0) = *(const uint4*)(O + b0);
+                } else {
+                    for (int b = (b0 > off ? b0 : off); b < (b1 < total ? b1 : total); b++) gdst[b] = O[b];
+                }
+            }
+        }
+        unit_bar(bar_id, G::UT);  // O is rewritten by the next item
+    }
+}
+
+}  // namespace pk
+
+// ------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------
+namespace {
+
+template <typename K>
+cudaError_t set_smem(K kern, size_t bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+inline unsigned grid_for(const Launcher& L, long long nitems, int units) {
+    long long ctas = (nitems + units - 1) / units;
+    if (ctas > L.sm_count) ctas = L.sm_count;
+    if (ctas < 1) ctas = 1;
+    return (unsigned)ctas;
+}
+
+template <int S, int LOG2N, int VEC, int MODE, int UNITS>
+cudaError_t run_c2c(const Launcher& L, const PassArgs& p) {
+    using G = pk::Geo<LOG2N, VEC>;
+    pk::C2CArgs a;
+    a.spec = p.spec; a.tw = p.tw; a.PW = p.PW; a.PH = p.PH; a.in_rows = p.in_rows; a.out_rows = p.out_rows;
+    a.nitems = MODE == pk::M_C2C_ROW ? (long long)p.nplanes * p.PH : (long long)p.nplanes * (p.PW / VEC);
+    const size_t smem = (G::L_BYTES + G::X_BYTES) * UNITS;
+    auto kern = pk::pencil_c2c<S, LOG2N, VEC, MODE, UNITS>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
+template <int LOG2N, int UNITS, bool INV>
+cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
+    using G = pk::Geo<LOG2N, 1>;
+    pk::U8Args a;
+    a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
+    a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.center = p.center;
+    a.nitems = (long long)(p.nplanes / 3) * p.H;
+    constexpr size_t UB = pk::U8Geo<LOG2N>::U_BYTES;
+    const size_t smem = (INV ? (G::L_BYTES + G::X_BYTES + UB) : (G::L_BYTES + 2 * UB)) * UNITS;
+    cudaError_t e;
+    if constexpr (INV) {
+        auto kern = pk::pencil_u8_inv<LOG2N, UNITS>;
+        if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+    } else {
+        auto kern = pk::pencil_u8_fwd<LOG2N, UNITS>;
+        if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+    }
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
+// per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB
+template <int LOG2N>
+struct Cfg;
+template <> struct Cfg<12> { static constexpr int ROW_UNITS = 2, COL_VEC = 2, COL_UNITS = 1, U8F_UNITS = 2, U8I_UNITS = 2; };
+template <> struct Cfg<11> { static constexpr int ROW_UNITS = 4, COL_VEC = 4, COL_UNITS = 1, U8F_UNITS = 4, U8I_UNITS = 4; };
+template <> struct Cfg<10> { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 2, U8F_UNITS = 8, U8I_UNITS = 8; };
+template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 4, U8F_UNITS = 8, U8I_UNITS = 8; };
+
+template <int LOG2N>
+cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
+    using C = Cfg<LOG2N>;
+    if (p.img_in) return run_u8<LOG2N, C::U8F_UNITS, false>(L, p);
+    if (p.img_out) return run_u8<LOG2N, C::U8I_UNITS, true>(L, p);
+    if (p.axis == 0)
+        return p.inverse ? run_c2c<-1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p)
+                         : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
+    return p.inverse ? run_c2c<-1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p)
+                     : run_c2c<+1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p);
+}
+
+}  // namespace
+
+cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* handled) {
+    *handled = true;
+    // the fused u8 passes need W <= PW == N (always true) and run along x only
+    switch (p.log2n) {
+        case 12: return dispatch<12>(L, p);
+        case 11: return dispatch<11>(L, p);
+        case 10: return dispatch<10>(L, p);
+        case 9: return dispatch<9>(L, p);
+        default: *handled = false; return cudaSuccess;
+    }
+}
+
 }  // namespace tfft

@@ -28,8 +28,9 @@ def assert_pixels(a, b):
     assert (d == 0).mean() >= PIX_EQ, f"only {(d == 0).mean():.6f} equal"
 
 
-@pytest.mark.parametrize("PH,PW,n", [(16, 16, 3), (32, 64, 2), (64, 16, 1), (128, 128, 4), (512, 512, 2), (256, 1024, 1),
-                                     (2048, 512, 1), (4096, 64, 1), (64, 8192, 1)])
+@pytest.mark.parametrize("PH,PW,n", [(16, 16, 3), (32, 64, 2), (64, 16, 1), (128, 128, 4), (512, 512, 5), (256, 1024, 1),
+                                     (2048, 512, 3), (4096, 64, 1), (64, 8192, 1), (1024, 2048, 2), (512, 4096, 1),
+                                     (4096, 1024, 1), (2048, 2048, 1)])
 def test_fft2d_matches_oracle(ctx, PH, PW, n):
     rng = np.random.default_rng(PH * 31 + PW)
     a = rng.standard_normal((n, PH, PW)) + 1j * rng.standard_normal((n, PH, PW))
@@ -89,7 +90,8 @@ def test_golden_embed_extract(ctx, name):
 
 @pytest.mark.parametrize("W,H,nbits,center,alpha", [
     (256, 256, 2480, False, 0.5), (512, 512, 60000, False, 0.5), (500, 300, 5000, True, 0.3),
-    (1024, 512, 30000, False, 0.18), (640, 480, 8000, False, 0.5)])
+    (1024, 512, 30000, False, 0.18), (640, 480, 8000, False, 0.5), (1100, 600, 20000, True, 0.5),
+    (2048, 1024, 50000, False, 0.5), (513, 1025, 9000, False, 0.5), (3000, 200, 4000, False, 0.5)])
 def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
     o = oracle()
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
