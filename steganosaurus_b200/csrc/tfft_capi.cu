@@ -321,7 +321,7 @@ int tfft_create(int device, tfft_ctx** out) {
     ctx->total_mem = tot;
     ctx->ws_limit = (size_t)((double)tot * 0.40);
     const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
-    ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : 1;
+    ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
     for (int i = 0; i < 2; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));

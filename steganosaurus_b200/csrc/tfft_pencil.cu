@@ -23,6 +23,8 @@
 // Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
 #include "tfft_kernels.cuh"
 
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 namespace tfft {
 namespace pk {
 
@@ -125,6 +127,37 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void unit_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// ---- TMA (cp.async.bulk.tensor) + mbarrier primitives ------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TFFT_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TFFT_MBAR_DONE;\n"
+        "bra TFFT_MBAR_WAIT;\n"
+        "TFFT_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                 ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+                 ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 __device__ __forceinline__ uint8_t clamp8(double v) {  // from_planes_u8 S:389
     double r = round(v);
@@ -236,7 +269,7 @@ struct C2CArgs {
 template <int S, int LOG2N, int VEC, int MODE, int UNITS>
 __global__ void __launch_bounds__(Geo<LOG2N, VEC>::UT* UNITS, 1) pencil_c2c(C2CArgs a) {
     using G = Geo<LOG2N, VEC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, ut = threadIdx.x % G::UT;
     const int c = ut % VEC, tt = ut / VEC;
     double2* L = (double2*)(smem_raw + (size_t)unit * (G::L_BYTES + G::X_BYTES));
@@ -296,6 +329,90 @@ __global__ void __launch_bounds__(Geo<LOG2N, VEC>::UT* UNITS, 1) pencil_c2c(C2CA
 }
 
 // ------------------------------------------------------------------------------------------
+// Column pass on the TMA engine.  One unit per CTA works on VEC adjacent columns
+// (N*VEC = 8192 elements: 128 KB landing buffer + 64 KB exchange/staging buffer, 512 threads).
+// Global traffic never touches the LSU: box loads {VEC complex x 256 rows} land the columns densely
+// as [row][column]; results are staged in X half a pencil at a time and leave through box stores.
+// Zero-structure: the load map only spans in_rows rows (TMA zero-fills the rest without reading),
+// the store map only spans out_rows rows (TMA clips the rest).
+// ------------------------------------------------------------------------------------------
+struct ColTmaArgs {
+    const double2* tw;
+    long long nitems;      // nplanes * PW / VEC
+    int groups_per_plane;  // PW / VEC
+};
+
+template <int S, int LOG2N, int VEC>
+__global__ void __launch_bounds__(512, 1) pencil_col_tma(const __grid_constant__ CUtensorMap in_map,
+                                                         const __grid_constant__ CUtensorMap out_map, ColTmaArgs a) {
+    using G = Geo<LOG2N, VEC>;
+    static_assert(G::UT == 512, "one 512-thread unit per CTA");
+    constexpr int BOX_ROWS = 256;
+    constexpr int NBOX = G::N / BOX_ROWS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar;
+    double2* L = (double2*)smem_raw;
+    double* X = (double*)(smem_raw + G::L_BYTES);
+    double2* STG = (double2*)X;  // staging view of X: (N/2) rows x VEC x 16 B
+    const int tid = threadIdx.x, c = tid % VEC, tt = tid / VEC;
+    const double scale = S < 0 ? 1.0 / (double)G::N : 1.0;  // S:357
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_load = [&](long long it) {
+        const int plane = (int)(it / a.groups_per_plane), g = (int)(it % a.groups_per_plane);
+        mbar_expect_tx(&full_bar, (unsigned)G::L_BYTES);
+#pragma unroll 1
+        for (int j = 0; j < NBOX; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
+    };
+
+    const long long stride = gridDim.x;
+    long long item = blockIdx.x;
+    if (tid == 0 && item < a.nitems) issue_load(item);
+    unsigned parity = 0;
+    for (; item < a.nitems; item += stride) {
+        mbar_wait(&full_bar, parity);
+        parity ^= 1;
+        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1);
+        __syncthreads();
+        double2 x[16];
+        stage2_load<LOG2N, VEC>(L, tt, c, x);
+        if (tid == 0) tma_wait_read_all();  // the previous item's last box store has finished reading X
+        __syncthreads();                    // L is free, X is free
+        if (tid == 0 && item + stride < a.nitems) {
+            fence_async_proxy();
+            issue_load(item + stride);
+        }
+        stage23<S, LOG2N, VEC>(X, tt, c, a.tw, x, 0);
+        const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            __syncthreads();  // h=0: every thread is past its last read of X; h=1: first half has been read out
+#pragma unroll
+            for (int k3 = 8 * h; k3 < 8 * h + 8; k3++) {
+                double2 v = x[oidx<16>(k3)];
+                v.x *= scale; v.y *= scale;
+                STG[(size_t)(tt + G::TP * (k3 - 8 * h)) * VEC + c] = v;
+            }
+            fence_async_proxy();
+            __syncthreads();
+            if (tid == 0) {
+#pragma unroll 1
+                for (int j = 0; j < NBOX / 2; j++)
+                    tma_store_3d(&out_map, STG + (size_t)j * BOX_ROWS * VEC, g * VEC * 2, h * (G::N / 2) + j * BOX_ROWS, plane);
+                tma_commit();
+                if (h == 0) tma_wait_read_all();
+            }
+        }
+    }
+    if (tid == 0) tma_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
 // u8 RGB row -> three forward row pencils.  item = (image, y < H)
 // ------------------------------------------------------------------------------------------
 struct U8Args {
@@ -318,7 +435,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd(U8A
     using G = Geo<LOG2N, 1>;
     constexpr size_t UB = U8Geo<LOG2N>::U_BYTES;
     constexpr size_t UNIT_BYTES = G::L_BYTES + 2 * UB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
     unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
     double2* L = (double2*)base;
@@ -376,7 +493,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv(U8A
     using G = Geo<LOG2N, 1>;
     constexpr size_t UB = U8Geo<LOG2N>::U_BYTES;
     constexpr size_t UNIT_BYTES = G::L_BYTES + G::X_BYTES + UB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
     unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
     double2* L = (double2*)base;
@@ -481,6 +598,55 @@ cudaError_t run_c2c(const Launcher& L, const PassArgs& p) {
     return cudaGetLastError();
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// planes viewed as doubles: [nplanes][rows][2*PW]; box = {2*VEC doubles, 256 rows, 1 plane}
+bool make_col_map(CUtensorMap* m, const double2* spec, int nplanes, int PH, int PW, int rows, int vec) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)2 * PW, (cuuint64_t)rows, (cuuint64_t)nplanes};
+    cuuint64_t strides[2] = {(cuuint64_t)PW * 16, (cuuint64_t)PH * PW * 16};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * vec), 256, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)spec, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int S, int LOG2N, int VEC>
+cudaError_t run_col_tma(const Launcher& L, const PassArgs& p, bool* ok) {
+    using G = pk::Geo<LOG2N, VEC>;
+    CUtensorMap in_map, out_map;
+    *ok = make_col_map(&in_map, p.spec, p.nplanes, p.PH, p.PW, p.in_rows, VEC) &&
+          make_col_map(&out_map, p.spec, p.nplanes, p.PH, p.PW, p.out_rows, VEC);
+    if (!*ok) return cudaSuccess;
+    pk::ColTmaArgs a;
+    a.tw = p.tw; a.groups_per_plane = p.PW / VEC; a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    const size_t smem = G::L_BYTES + G::X_BYTES;
+    auto kern = pk::pencil_col_tma<S, LOG2N, VEC>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, a);
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
 template <int LOG2N, int UNITS, bool INV>
 cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
     using G = pk::Geo<LOG2N, 1>;
@@ -507,10 +673,10 @@ cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
 // per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB
 template <int LOG2N>
 struct Cfg;
-template <> struct Cfg<12> { static constexpr int ROW_UNITS = 2, COL_VEC = 2, COL_UNITS = 1, U8F_UNITS = 2, U8I_UNITS = 2; };
-template <> struct Cfg<11> { static constexpr int ROW_UNITS = 4, COL_VEC = 4, COL_UNITS = 1, U8F_UNITS = 4, U8I_UNITS = 4; };
-template <> struct Cfg<10> { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 2, U8F_UNITS = 8, U8I_UNITS = 8; };
-template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 4, U8F_UNITS = 8, U8I_UNITS = 8; };
+template <> struct Cfg<12> { static constexpr int ROW_UNITS = 2, COL_VEC = 2, COL_UNITS = 1, U8F_UNITS = 2, U8I_UNITS = 2, TMA_VEC = 2; };
+template <> struct Cfg<11> { static constexpr int ROW_UNITS = 4, COL_VEC = 4, COL_UNITS = 1, U8F_UNITS = 4, U8I_UNITS = 4, TMA_VEC = 4; };
+template <> struct Cfg<10> { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 2, U8F_UNITS = 8, U8I_UNITS = 8, TMA_VEC = 8; };
+template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, COL_UNITS = 4, U8F_UNITS = 8, U8I_UNITS = 8, TMA_VEC = 16; };
 
 template <int LOG2N>
 cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
@@ -520,6 +686,11 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     if (p.axis == 0)
         return p.inverse ? run_c2c<-1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p)
                          : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
+    if (L.fft_impl != 2 && p.PW >= C::TMA_VEC) {  // TFFT_FFT_IMPL=lsu keeps the cp.async/STG column kernel
+        bool ok = false;
+        cudaError_t e = p.inverse ? run_col_tma<-1, LOG2N, C::TMA_VEC>(L, p, &ok) : run_col_tma<+1, LOG2N, C::TMA_VEC>(L, p, &ok);
+        if (e != cudaSuccess || ok) return e;
+    }
     return p.inverse ? run_c2c<-1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p)
                      : run_c2c<+1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p);
 }
