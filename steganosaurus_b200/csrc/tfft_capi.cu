@@ -56,7 +56,7 @@ struct tfft_ctx {
 
 namespace {
 
-constexpr uint32_t CAND_CAP = 1u << 16;
+constexpr uint32_t CAND_CAP = 1u << 19;  // median: sample (<= 2^18 keys) and bracket members per plane
 constexpr int MAX_CHUNK = 64;
 
 int fail_cuda(tfft_ctx* c, cudaError_t e, const char* where) {

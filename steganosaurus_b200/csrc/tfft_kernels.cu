@@ -178,9 +178,8 @@ cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a) {
 // --------------------------------------------------------------------------------------------
 // Median of |F| (median_abs S:404-409): exact selection of the element of rank P/2 by an MSB
 // radix select on the IEEE bit pattern of hypot(re,im) (non-negative doubles order like
-// unsigned integers).  Two 11-bit histogram passes narrow the key to a 22-bit prefix; the
-// survivors are compacted and finished by one CTA per plane.  If the survivors do not fit
-// (degenerate spectra with massively repeated magnitudes) further full histogram passes run.
+// unsigned integers).  Generic path: six 11-bit histogram passes over the plane (always exact,
+// used as the on-device fallback).  Fast path: see "sampled bracket" below.
 // --------------------------------------------------------------------------------------------
 constexpr int RADIX_BITS = 11;
 constexpr int RADIX = 1 << RADIX_BITS;
@@ -196,7 +195,7 @@ __device__ __forceinline__ uint64_t mag_key(double2 z) {
 size_t median_work_bytes(int nplanes, uint32_t cand_cap) {
     size_t b = 0;
     b += (size_t)nplanes * RADIX * sizeof(uint32_t);
-    b += (size_t)nplanes * sizeof(uint64_t) * 3;  // prefix, rank, counts
+    b += (size_t)nplanes * sizeof(uint64_t) * 5;  // prefix, rank, counts, bracket (2)
     b += (size_t)nplanes * cand_cap * sizeof(uint64_t);
     b += (size_t)(nplanes + 4) * sizeof(uint32_t);  // cand_n + fallback flag
     return (b + 255) & ~(size_t)255;
@@ -206,6 +205,7 @@ void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap
     w.prefix = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
     w.rank = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
     w.counts = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
+    w.prefix2 = (uint64_t*)p; p += (size_t)nplanes * 2 * sizeof(uint64_t);
     w.cand = (uint64_t*)p; p += (size_t)nplanes * cand_cap * sizeof(uint64_t);
     w.hist = (uint32_t*)p; p += (size_t)nplanes * RADIX * sizeof(uint32_t);
     w.cand_n = (uint32_t*)p;
@@ -260,65 +260,209 @@ __global__ void median_pick(int d, MedianWork w, const int* gate) {
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) w.hist[ip * RADIX + i] = 0;
 }
 
-// compact the keys matching the first `d` digits (only if they fit cand_cap)
-__global__ void __launch_bounds__(512) median_compact(const double2* __restrict__ spec, uint64_t P, int d, MedianWork w, uint32_t* fill) {
-    const int ip = blockIdx.y;
-    if (w.cand_n[ip] > w.cand_cap) return;
-    const double2* pl = spec + (size_t)ip * P;
-    const int hi_sft = key_shift(d - 1);
-    const uint64_t prefix = w.prefix[ip] >> hi_sft;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t k = mag_key(pl[i]);
-        if ((k >> hi_sft) == prefix) {
-            uint32_t slot = atomicAdd(&fill[ip], 1u);
-            if (slot < w.cand_cap) w.cand[(size_t)ip * w.cand_cap + slot] = k;
-        }
-    }
-}
-
-// finish on the compacted list: one CTA per plane runs the remaining digits locally.
-__global__ void __launch_bounds__(1024) median_finish(int d0, MedianWork w, double* median) {
-    __shared__ uint32_t sh[RADIX];
-    __shared__ uint64_t s_prefix, s_rank;
-    const int ip = blockIdx.x;
-    const uint32_t n = w.cand_n[ip];
-    if (n > w.cand_cap) return;  // handled by the full-pass fallback
-    const uint64_t* c = w.cand + (size_t)ip * w.cand_cap;
-    if (threadIdx.x == 0) { s_prefix = w.prefix[ip]; s_rank = w.rank[ip]; }
-    for (int d = d0; d < NUM_DIGITS; d++) {
-        for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
-        __syncthreads();
-        const int sft = key_shift(d), wid = key_width(d), hi_sft = sft + wid;
-        const uint64_t prefix = s_prefix;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint64_t k = c[i];
-            if ((k >> hi_sft) == (prefix >> hi_sft)) atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint64_t r = s_rank;
-            int b = 0;
-            for (; b < (1 << wid) - 1; b++) {
-                if (r < sh[b]) break;
-                r -= sh[b];
-            }
-            s_rank = r;
-            s_prefix = prefix | ((uint64_t)b << sft);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) median[ip] = __longlong_as_double((long long)s_prefix);
-}
-
-// fallback completion when the survivors did not fit: prefix is complete after all digits
+// generic path completion: the prefix is complete after all digits
 __global__ void median_from_prefix(MedianWork w, double* median, int nplanes, const int* gate) {
     if (!*gate) return;
     int ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (ip < nplanes) median[ip] = __longlong_as_double((long long)w.prefix[ip]);  // exact for every plane
 }
-__global__ void any_overflow(MedianWork w, int nplanes, int* flag) {
-    int ip = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip < nplanes && w.cand_n[ip] > w.cand_cap) *flag = 1;
+// ---- fast path: sampled bracket + one exact scan ---------------------------------------------
+// (1) a strided sample of |F| gives two order statistics lo <= hi that bracket the median with
+// overwhelming probability; (2) ONE pass over the plane counts the elements strictly below the
+// bracket and compacts the few (~1 %) inside it -- membership is decided on q = re^2+im^2 (two
+// FP64 instructions) against thresholds widened by 1e-9, hypot() is only evaluated for members;
+// (3) one CTA per plane selects the exact element of rank P/2 - below among the members.  The
+// result is the same double median_abs (S:404-409) returns.  Whenever the bracket misses or the
+// members do not fit (flat images, adversarial spectra) a device-side flag routes the plane
+// batch through the generic radix passes above -- the answer is exact either way.
+constexpr uint32_t SAMPLE_MAX = 1u << 18;
+constexpr uint32_t RANK_GUARD = 8;
+
+struct Bracket { double qlo, qhi; };
+
+// block-wide exact selection of the key of rank `rank` (0-based) among n keys (blockDim.x == 1024).
+// The bits shared by every key (clz(min ^ max)) are skipped, the rest is consumed 11 bits at a time
+// with a shared-memory histogram and a parallel bucket search.
+struct SelectScratch {
+    uint32_t hist[RADIX];
+    uint32_t warp_tot[32];
+    uint64_t red[64];
+    uint64_t prefix, rank;
+    int top;
+};
+__device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint64_t rank, SelectScratch* sc) {
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    // min / max
+    uint64_t mn = ~0ull, mx = 0;
+    for (uint32_t i = tid; i < n; i += blockDim.x) { const uint64_t k = c[i]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+    for (int o = 16; o; o >>= 1) {
+        const uint64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn; mx = b2 > mx ? b2 : mx;
+    }
+    if (lane == 0) { sc->red[wrp] = mn; sc->red[32 + wrp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w2 = 1; w2 < (int)(blockDim.x >> 5); w2++) { mn = sc->red[w2] < mn ? sc->red[w2] : mn; mx = sc->red[32 + w2] > mx ? sc->red[32 + w2] : mx; }
+        const uint64_t diff = mn ^ mx;
+        sc->top = diff ? 64 - __clzll((long long)diff) : 0;  // number of low bits that still vary
+        sc->prefix = sc->top == 64 ? 0 : (mn >> sc->top) << sc->top;
+        sc->rank = rank;
+    }
+    __syncthreads();
+    while (true) {
+        const int top = sc->top;
+        if (top == 0) break;
+        const int wid = top < RADIX_BITS ? top : RADIX_BITS, sft = top - wid;
+        const uint64_t prefix = sc->prefix;
+        for (int i = tid; i < RADIX; i += blockDim.x) sc->hist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const uint64_t k = c[i];
+            if (top == 64 || (k >> top) == (prefix >> top)) atomicAdd(&sc->hist[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
+        }
+        __syncthreads();
+        // parallel bucket search: thread t owns bins 2t, 2t+1
+        const uint32_t h0 = sc->hist[2 * tid], h1 = sc->hist[2 * tid + 1];
+        uint32_t incl = h0 + h1;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) sc->warp_tot[wrp] = incl;
+        __syncthreads();
+        if (wrp == 0) {
+            uint32_t t = sc->warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += v; }
+            sc->warp_tot[lane] = t;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint64_t r = sc->rank;
+        const uint64_t excl = (uint64_t)(wrp ? sc->warp_tot[wrp - 1] : 0) + (incl - h0 - h1);
+        __syncthreads();
+        if (r >= excl && r < excl + h0 + h1) {  // exactly one thread
+            const int bkt = (r < excl + h0) ? 2 * tid : 2 * tid + 1;
+            sc->rank = r - (bkt == 2 * tid ? excl : excl + h0);
+            sc->prefix = prefix | ((uint64_t)bkt << sft);
+            sc->top = sft;
+        }
+        __syncthreads();
+    }
+    const uint64_t res = sc->prefix;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(256) median_sample(const double2* __restrict__ spec, uint64_t P, uint32_t S, uint64_t stride, MedianWork w) {
+    const int ip = blockIdx.y;
+    const double2* pl = spec + (size_t)ip * P;
+    // stratified pseudo-random positions: one element per stride block at a hashed offset (a fixed
+    // offset would alias with the periodic leakage pattern that zero padding imprints on the spectrum)
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < S; j += gridDim.x * blockDim.x) {
+        uint32_t h = (j + 0x9E3779B9u * (uint32_t)(ip + 1)) * 2654435761u;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        w.cand[(size_t)ip * w.cand_cap + j] = mag_key(pl[(uint64_t)j * stride + (uint64_t)(h % (uint32_t)stride)]);
+    }
+}
+
+// one CTA per plane.  exact != 0: the "sample" is the whole plane -> select the median directly.
+__global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, uint64_t P, int exact, Bracket* br, double* median) {
+    __shared__ SelectScratch sc;
+    const int ip = blockIdx.x;
+    const uint64_t* c = w.cand + (size_t)ip * w.cand_cap;
+    if (exact) {
+        const uint64_t k = select_rank(c, S, P / 2, &sc);
+        if (threadIdx.x == 0) { median[ip] = __longlong_as_double((long long)k); w.cand_n[ip] = 0; }
+        return;
+    }
+    // sample quantile 0.5 +- 6 sigma, sigma = 0.5/sqrt(S)
+    const double delta = 3.0 / sqrt((double)S);
+    long long rlo = (long long)floor((0.5 - delta) * S), rhi = (long long)ceil((0.5 + delta) * S);
+    if (rlo < 0) rlo = 0;
+    if (rhi > (long long)S - 1) rhi = S - 1;
+    const uint64_t klo = select_rank(c, S, (uint64_t)rlo, &sc);
+    const uint64_t khi = select_rank(c, S, (uint64_t)rhi, &sc);
+    if (threadIdx.x == 0) {
+        const double lo = __longlong_as_double((long long)klo), hi = __longlong_as_double((long long)khi);
+        br[ip].qlo = lo * lo * (1.0 - 1e-9);
+        br[ip].qhi = hi * hi * (1.0 + 1e-9);
+        w.cand_n[ip] = 0;  // becomes the member fill counter
+    }
+}
+
+constexpr int SCAN_UNROLL = 4;
+constexpr uint32_t SCAN_SBUF = 3072;  // members staged per CTA before one global reservation (24 KB)
+__global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ spec, uint64_t P, MedianWork w, const Bracket* __restrict__ br) {
+    __shared__ uint64_t s_buf[SCAN_SBUF];
+    __shared__ unsigned s_cnt, s_base, ws[16];
+    const int ip = blockIdx.y;
+    const double2* pl = spec + (size_t)ip * P;
+    const double qlo = br[ip].qlo, qhi = br[ip].qhi;
+    uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned below = 0;
+    const int lane = threadIdx.x & 31;
+    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
+    // each CTA owns a contiguous span so that the SCAN_UNROLL loads of a thread are independent
+    const uint64_t per_cta = (P + gridDim.x - 1) / gridDim.x;
+    const uint64_t lo = (uint64_t)blockIdx.x * per_cta, hi = lo + per_cta < P ? lo + per_cta : P;
+    (void)step;
+    for (uint64_t base = lo; base < hi; base += (uint64_t)blockDim.x * SCAN_UNROLL) {
+        double2 z[SCAN_UNROLL];
+        bool inb[SCAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
+            inb[u] = i < hi;
+            z[u] = inb[u] ? pl[i] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const double q = fma(z[u].x, z[u].x, z[u].y * z[u].y);
+            const bool member = inb[u] && q >= qlo && q <= qhi;
+            if (inb[u] && q < qlo) below++;
+            const unsigned m = __ballot_sync(0xffffffffu, member);
+            if (m) {
+                unsigned b0 = 0;
+                if (lane == 0) b0 = atomicAdd(&s_cnt, (unsigned)__popc(m));
+                b0 = __shfl_sync(0xffffffffu, b0, 0);
+                if (member) {
+                    const unsigned slot = b0 + __popc(m & ((1u << lane) - 1));
+                    const uint64_t key = mag_key(z[u]);
+                    if (slot < SCAN_SBUF) s_buf[slot] = key;
+                    else {  // staging full (pathological density): reserve directly
+                        const unsigned g = atomicAdd(&w.cand_n[ip], 1u);
+                        if (g < w.cand_cap) cand[g] = key;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o; o >>= 1) below += __shfl_down_sync(0xffffffffu, below, o);
+    if (lane == 0) ws[threadIdx.x >> 5] = below;
+    __syncthreads();
+    const unsigned nloc = s_cnt < SCAN_SBUF ? s_cnt : SCAN_SBUF;
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += ws[k];
+        if (t) atomicAdd((unsigned long long*)&w.counts[ip], t);
+        s_base = nloc ? atomicAdd(&w.cand_n[ip], nloc) : 0;
+    }
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < nloc; i += blockDim.x)
+        if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
+}
+
+// one CTA per plane: exact rank among the members, or raise the fallback flag
+__global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, double* median, int* flag) {
+    __shared__ SelectScratch sc;
+    const int ip = blockIdx.x;
+    const uint32_t n = w.cand_n[ip];
+    const uint64_t below = w.counts[ip], rank = P / 2;
+    const bool ok = n <= w.cand_cap && rank >= below + RANK_GUARD && rank + RANK_GUARD < below + n;
+    if (!ok) {
+        if (threadIdx.x == 0) *flag = 1;
+        return;
+    }
+    const uint64_t k = select_rank(w.cand + (size_t)ip * w.cand_cap, n, rank - below, &sc);
+    if (threadIdx.x == 0) median[ip] = __longlong_as_double((long long)k);
 }
 
 // Capacity count (S:999-1007): annulus bins in index space (radius from bin (0,0), scaled by
@@ -365,31 +509,27 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     const dim3 grid((unsigned)(chunks > 592 ? 592 : chunks), (unsigned)nplanes);
     median_init<<<(nplanes * RADIX + 255) / 256, 256, 0, L.stream>>>(w, nplanes, P);
     TFFT_LAUNCH_CHECK(L);
-    // two full histogram passes -> 22-bit prefix
-    for (int d = 0; d < 2; d++) {
-        median_hist<<<grid, 512, 0, L.stream>>>(spec, P, d, w, nullptr);
-        TFFT_LAUNCH_CHECK(L);
-        median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, nullptr);
-        TFFT_LAUNCH_CHECK(L);
-    }
-    // compaction of the survivors + local finish.  `fill` reuses counts[] storage (uint32 view)
-    // before the capacity kernel needs it; it is re-zeroed afterwards.
-    uint32_t* fill = (uint32_t*)w.counts;
-    median_compact<<<grid, 512, 0, L.stream>>>(spec, P, 2, w, fill);
+    int* d_flag = (int*)(w.cand_n + nplanes);  // one spare word after cand_n (see median_work_bytes)
+    Bracket* br = (Bracket*)w.prefix2;
+    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), L.stream);
+    if (e != cudaSuccess) return e;
+    const bool exact = P <= (uint64_t)w.cand_cap && P <= (uint64_t)SAMPLE_MAX;
+    const uint32_t S = exact ? (uint32_t)P : (SAMPLE_MAX < w.cand_cap ? SAMPLE_MAX : w.cand_cap);
+    const uint64_t stride = exact ? 1 : P / S;
+    median_sample<<<dim3((S + 255) / 256 > 256 ? 256 : (S + 255) / 256, (unsigned)nplanes), 256, 0, L.stream>>>(spec, P, S, stride, w);
     TFFT_LAUNCH_CHECK(L);
-    median_finish<<<nplanes, 1024, 0, L.stream>>>(2, w, d_median);
+    median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, P, exact ? 1 : 0, br, d_median);
     TFFT_LAUNCH_CHECK(L);
-    // Degenerate fallback (survivors > cand_cap, e.g. flat images whose spectrum is all zeros):
-    // finish every plane with full histogram passes.  The decision stays on the device -- the
-    // extra kernels are gated by a flag and exit immediately in the normal case (no host sync).
-    {
-        int* d_flag = (int*)(w.cand_n + nplanes);  // one spare word after cand_n (see median_work_bytes)
-        cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), L.stream);
-        if (e != cudaSuccess) return e;
-        any_overflow<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, nplanes, d_flag);
+    if (!exact) {
+        median_scan<<<grid, 512, 0, L.stream>>>(spec, P, w, br);
         TFFT_LAUNCH_CHECK(L);
-        for (int d = 2; d < NUM_DIGITS; d++) {
-            median_hist<<<grid, 512, 0, L.stream>>>(spec, P, d, w, d_flag);
+        median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, d_median, d_flag);
+        TFFT_LAUNCH_CHECK(L);
+        // Fallback, decided on the device (no host sync): the generic radix passes are gated by the
+        // flag and exit immediately in the normal case.
+        const dim3 fgrid(8, (unsigned)nplanes);  // rarely does real work: keep the gated launches cheap
+        for (int d = 0; d < NUM_DIGITS; d++) {
+            median_hist<<<fgrid, 512, 0, L.stream>>>(spec, P, d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
             median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
@@ -397,7 +537,7 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         median_from_prefix<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, d_median, nplanes, d_flag);
         TFFT_LAUNCH_CHECK(L);
     }
-    cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
+    e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
     if (e != cudaSuccess) return e;
     if (d_usable) {
         const int m = PH < PW ? PH : PW;

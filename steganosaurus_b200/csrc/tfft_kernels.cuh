@@ -53,7 +53,8 @@ struct MedianWork {
     uint64_t* cand;      // [nplanes][cand_cap] candidate keys
     uint32_t* cand_n;    // [nplanes]
     uint32_t cand_cap;
-    uint64_t* counts;    // [nplanes] capacity counts before halving
+    uint64_t* counts;    // [nplanes] below-bracket counts, then capacity counts before halving
+    uint64_t* prefix2;   // [nplanes][2] median bracket (qlo, qhi as doubles)
 };
 size_t median_work_bytes(int nplanes, uint32_t cand_cap);
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);

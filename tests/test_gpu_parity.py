@@ -181,6 +181,38 @@ def test_degenerate_flat_image(ctx):
     assert_pixels(stego[0], want["stego"])
 
 
+@pytest.mark.parametrize("kind", ["flat", "half_flat", "two_level"])
+def test_median_fallback_large_plane(ctx, kind):
+    """Planes larger than the sample (P > 2^18) with massively tied magnitudes: the sampled bracket
+    cannot isolate the median, the device-side fallback (generic radix passes) must give the exact value."""
+    H = W = 1024
+    img = np.full((H, W, 3), 100, np.uint8)
+    if kind == "half_flat":
+        img[:, W // 2:, :] = synth.gen_texture(W // 2, H, 3)
+    elif kind == "two_level":
+        img[::2, :, 1] = 30
+    o = O.port()
+    F = o.forward_spectrum(img)
+    wmed = np.array([o.median_abs(F[p]) for p in range(3)])
+    wus = sum(o.count_plane(F[p], 0.05, 0.45, 0.01 * wmed[p]) for p in range(3))
+    stego, usable, med = ctx.embed_batch(img[None], np.zeros(0, np.uint32), np.zeros((1, 0), np.uint8))
+    assert np.allclose(med[0], wmed, rtol=1e-9, atol=1e-7), (med, wmed)
+    assert int(usable[0]) == wus
+
+
+def test_median_exact_many_planes(ctx):
+    """Exact medians (bit-for-bit the selected element) for a batch, against numpy on the GPU spectrum itself."""
+    W, H = 1536, 1100
+    imgs = np.stack([synth.gen_texture(W, H, 50 + i) for i in range(3)])
+    _, _, med = ctx.embed_batch(imgs, np.zeros(0, np.uint32), np.zeros((3, 0), np.uint8))
+    for i in range(3):
+        F = ctx.forward_spectrum(imgs[i])
+        for p in range(3):
+            mags = np.hypot(F[p].real, F[p].imag).ravel()
+            want = np.partition(mags, mags.size // 2)[mags.size // 2]
+            assert abs(med[i, p] - want) <= 4e-16 * want, (i, p, med[i, p], want)
+
+
 def test_read_ties(ctx):
     """read_bit_from_bin ties -> 1: a flat image has exact zeros in the annulus."""
     cover = np.zeros((32, 32, 3), np.uint8)
