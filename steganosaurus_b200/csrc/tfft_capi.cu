@@ -24,8 +24,11 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf spec, in, out, bits, med, medians, usable, outbytes, raw;
-    uint64_t* h_usable = nullptr;  // pinned staging for the capacity verdict
-    size_t h_usable_cap = 0;
+    // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
+    // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
+    // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
+    unsigned char* h_stage = nullptr;
+    size_t h_stage_cap = 0;
 };
 
 }  // namespace
@@ -58,6 +61,7 @@ namespace {
 
 constexpr uint32_t CAND_CAP = 1u << 19;  // median: sample (<= 2^18 keys) and bracket members per plane
 constexpr int MAX_CHUNK = 64;
+constexpr int HOST_CHUNK = 16;  // host-buffer entry points: small chunks so H2D / kernels / D2H of neighbouring chunks overlap
 
 int fail_cuda(tfft_ctx* c, cudaError_t e, const char* where) {
     snprintf(c->cuda_err, sizeof(c->cuda_err), "%.160s: %.80s", where, cudaGetErrorString(e));
@@ -170,11 +174,15 @@ int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, 
     }
     if (outbytes && (rc = ensure(ctx, S.outbytes, (size_t)chunk * outbytes))) return rc;
     if (rawbytes && (rc = ensure(ctx, S.raw, (size_t)chunk * rawbytes))) return rc;
-    if (S.h_usable_cap < (size_t)chunk) {
-        if (S.h_usable) cudaFreeHost(S.h_usable);
-        CK(cudaHostAlloc((void**)&S.h_usable, sizeof(uint64_t) * MAX_CHUNK, cudaHostAllocDefault));
-        S.h_usable_cap = MAX_CHUNK;
-    }
+    return TFFT_OK;
+}
+
+int ensure_stage(tfft_ctx* ctx, Slot& S, size_t bytes) {
+    if (bytes <= S.h_stage_cap) return TFFT_OK;
+    if (S.h_stage) cudaFreeHost(S.h_stage);
+    S.h_stage = nullptr; S.h_stage_cap = 0;
+    CK(cudaHostAlloc((void**)&S.h_stage, bytes, cudaHostAllocDefault));
+    S.h_stage_cap = bytes;
     return TFFT_OK;
 }
 
@@ -339,7 +347,7 @@ void tfft_destroy(tfft_ctx* ctx) {
         Slot& S = ctx->slot[i];
         release(S.spec); release(S.in); release(S.out); release(S.bits); release(S.med);
         release(S.medians); release(S.usable); release(S.outbytes); release(S.raw);
-        if (S.h_usable) cudaFreeHost(S.h_usable);
+        if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
     release(ctx->bins); release(ctx->jitter);
@@ -420,28 +428,37 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = chunk_for(ctx, g, n, 2);
+    const int chunk = std::min(chunk_for(ctx, g, n, 2), HOST_CHUNK);
     const int nslots = (n > chunk) ? 2 : 1;
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
+    const size_t stage_bytes = (size_t)chunk * (sizeof(uint64_t) + 3 * sizeof(double));
+    for (int s = 0; s < nslots; s++)
+        if ((rc = ensure_stage(ctx, ctx->slot[s], stage_bytes))) return rc;
     bool over = false;
+    int pend_i0[2] = {-1, -1}, pend_m[2] = {0, 0};
+    auto drain = [&](int s) -> int {  // wait for the slot's chunk and hand its small results to the caller
+        if (pend_i0[s] < 0) return TFFT_OK;
+        Slot& S = ctx->slot[s];
+        CK(cudaStreamSynchronize(S.stream));
+        const uint64_t* hu = (const uint64_t*)S.h_stage;
+        const double* hm = (const double*)(S.h_stage + (size_t)chunk * sizeof(uint64_t));
+        for (int k = 0; k < pend_m[s]; k++) {
+            if (usable) usable[pend_i0[s] + k] = hu[k];
+            if (hu[k] < (uint64_t)nbits) over = true;
+        }
+        if (median) memcpy(median + (size_t)pend_i0[s] * 3, hm, sizeof(double) * 3 * pend_m[s]);
+        pend_i0[s] = -1;
+        return TFFT_OK;
+    };
     int ci = 0;
-    std::vector<int> pending_i0[2], pending_m[2];
     for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
-        Slot& S = ctx->slot[ci & 1];
+        const int sl = ci & 1;
+        Slot& S = ctx->slot[sl];
         const int m = std::min(chunk, n - i0);
         cudaStream_t st = S.stream;
-        // the pinned verdict buffer of this slot is about to be overwritten: drain it first
-        if (!pending_i0[ci & 1].empty()) {
-            CK(cudaStreamSynchronize(st));
-            const int p0 = pending_i0[ci & 1].back(), pm = pending_m[ci & 1].back();
-            for (int k = 0; k < pm; k++) {
-                if (usable) usable[p0 + k] = S.h_usable[k];
-                if (S.h_usable[k] < (uint64_t)nbits) over = true;
-            }
-            pending_i0[ci & 1].clear(); pending_m[ci & 1].clear();
-        }
+        if ((rc = drain(sl))) return rc;  // the slot's buffers are about to be reused
         CK(cudaMemcpyAsync(S.in.p, cover + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
         if (nbits) CK(cudaMemcpyAsync(S.bits.p, bits + (size_t)i0 * nbits, (size_t)m * nbits, cudaMemcpyHostToDevice, st));
         Launcher L = make_launcher(ctx, st);
@@ -450,20 +467,12 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
                          (uint8_t*)S.out.p, (uint64_t*)S.usable.p, (double*)S.medians.p);
         if (rc) return rc;
         CK(cudaMemcpyAsync(stego + (size_t)i0 * g.img_bytes, S.out.p, (size_t)m * g.img_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(S.h_usable, S.usable.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
-        if (median) CK(cudaMemcpyAsync(median + (size_t)i0 * 3, S.medians.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
-        pending_i0[ci & 1].push_back(i0); pending_m[ci & 1].push_back(m);
+        CK(cudaMemcpyAsync(S.h_stage, S.usable.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(S.h_stage + (size_t)chunk * sizeof(uint64_t), S.medians.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
+        pend_i0[sl] = i0; pend_m[sl] = m;
     }
-    for (int s = 0; s < 2; s++) {
-        if (pending_i0[s].empty()) continue;
-        Slot& S = ctx->slot[s];
-        CK(cudaStreamSynchronize(S.stream));
-        const int p0 = pending_i0[s].back(), pm = pending_m[s].back();
-        for (int k = 0; k < pm; k++) {
-            if (usable) usable[p0 + k] = S.h_usable[k];
-            if (S.h_usable[k] < (uint64_t)nbits) over = true;
-        }
-    }
+    for (int s = 0; s < 2; s++)
+        if ((rc = drain(s))) return rc;
     return over ? TFFT_E_CAPACITY : TFFT_OK;
 }
 
@@ -506,7 +515,7 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = chunk_for(ctx, g, n, 2);
+    const int chunk = std::min(chunk_for(ctx, g, n, 2), HOST_CHUNK);
     const int nslots = (n > chunk) ? 2 : 1;
     const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
     const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
@@ -514,11 +523,26 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, 0, (out ? nb : 0) + (out_payload ? nbp : 0), raw_bits ? nbins : 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbins, jitter, ctx->slot[0].stream))) return rc;
+    const size_t per_img = (out ? nb : 0) + (out_payload ? nbp : 0);
+    for (int s = 0; s < nslots; s++)
+        if (per_img && (rc = ensure_stage(ctx, ctx->slot[s], (size_t)chunk * per_img))) return rc;
+    int pend_i0[2] = {-1, -1}, pend_m[2] = {0, 0};
+    auto drain = [&](int s) -> int {
+        if (pend_i0[s] < 0) return TFFT_OK;
+        Slot& S = ctx->slot[s];
+        CK(cudaStreamSynchronize(S.stream));
+        if (out && nb) memcpy(out + (size_t)pend_i0[s] * nb, S.h_stage, (size_t)pend_m[s] * nb);
+        if (out_payload && nbp) memcpy(out_payload + (size_t)pend_i0[s] * nbp, S.h_stage + (out ? (size_t)chunk * nb : 0), (size_t)pend_m[s] * nbp);
+        pend_i0[s] = -1;
+        return TFFT_OK;
+    };
     int ci = 0;
     for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
-        Slot& S = ctx->slot[ci & 1];
+        const int sl = ci & 1;
+        Slot& S = ctx->slot[sl];
         const int m = std::min(chunk, n - i0);
         cudaStream_t st = S.stream;
+        if ((rc = drain(sl))) return rc;
         CK(cudaMemcpyAsync(S.in.p, stego + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
         Launcher L = make_launcher(ctx, st);
         uint8_t* d_out = out ? (uint8_t*)S.outbytes.p : nullptr;
@@ -527,11 +551,13 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
                            jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, d_out, d_pay,
                            raw_bits ? (uint8_t*)S.raw.p : nullptr);
         if (rc) return rc;
-        if (d_out && nb) CK(cudaMemcpyAsync(out + (size_t)i0 * nb, d_out, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
-        if (d_pay && nbp) CK(cudaMemcpyAsync(out_payload + (size_t)i0 * nbp, d_pay, (size_t)m * nbp, cudaMemcpyDeviceToHost, st));
+        if (d_out && nb) CK(cudaMemcpyAsync(S.h_stage, d_out, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
+        if (d_pay && nbp) CK(cudaMemcpyAsync(S.h_stage + (out ? (size_t)chunk * nb : 0), d_pay, (size_t)m * nbp, cudaMemcpyDeviceToHost, st));
         if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits + (size_t)i0 * nbins, S.raw.p, (size_t)m * nbins, cudaMemcpyDeviceToHost, st));
+        pend_i0[sl] = i0; pend_m[sl] = m;
     }
-    for (int s = 0; s < nslots; s++) CK(cudaStreamSynchronize(ctx->slot[s].stream));
+    for (int s = 0; s < 2; s++)
+        if ((rc = drain(s))) return rc;
     return TFFT_OK;
 }
 
