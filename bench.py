@@ -348,8 +348,9 @@ def run_ours(args):
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            if tj.get("kernel") == name:
-                traffic = tj.get("dram_bytes_per_launch")
+            if tj.get("kernel") == name and groups:
+                # ncu-measured DRAM bytes per image x images in one launch group of this run
+                traffic = tj["dram_bytes_per_image"] * (B * args.steps * (2 if name in ("row_fwd_u8", "col_fwd") else 1)) / groups
         except Exception:
             pass
     mp_per_step = B * W * H / 1e6
