@@ -44,6 +44,9 @@ struct tfft_ctx {
     DevBuf bins, jitter;
     uint64_t launches = 0;
     int fft_impl = 1;
+    bool use_half = true;   // real-input symmetry (half-spectrum workspace); TFFT_SPECTRUM=full disables
+    DevBuf full;            // expansion target of the tfft_forward_spectrum hook
+    SpecLayout res_lay{0, 0, 0, 0};
     // resident spectra for the two-phase extract
     int res_n = 0, res_PH = 0, res_PW = 0;
     char cuda_err[256] = {0};
@@ -95,8 +98,11 @@ struct Geom {
     int W, H, PW, PH, lw, lh;
     size_t P;          // PH*PW
     size_t img_bytes;  // H*W*3
+    int half, ld;      // workspace layout (SpecLayout)
+    size_t E;          // stored elements per plane = PH*ld
+    SpecLayout lay() const { return SpecLayout{PH, PW, ld, half}; }
 };
-int make_geom(int W, int H, Geom& g) {
+int make_geom(const tfft_ctx* ctx, int W, int H, Geom& g) {
     if (W <= 0 || H <= 0) return TFFT_E_INVALID;
     g.W = W; g.H = H;
     g.PW = next_pow2_i(W); g.PH = next_pow2_i(H);  // S:394
@@ -107,6 +113,10 @@ int make_geom(int W, int H, Geom& g) {
     g.lw = ilog2(g.PW); g.lh = ilog2(g.PH);
     g.P = (size_t)g.PW * g.PH;
     g.img_bytes = (size_t)W * H * 3;
+    // half-spectrum workspace whenever both axes run on the pencil kernels (512..4096 points)
+    g.half = (ctx && ctx->use_half && ctx->fft_impl != 0 && g.lw >= 9 && g.lw <= 12 && g.lh >= 9 && g.lh <= 12) ? 1 : 0;
+    g.ld = g.half ? g.PW / 2 + 16 : g.PW;
+    g.E = (size_t)g.PH * g.ld;
     return TFFT_OK;
 }
 
@@ -152,7 +162,7 @@ void prof_drain(tfft_ctx* c) {
 
 // images per chunk so that `nslots` spectrum workspaces fit the limit
 int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
-    const size_t per_img = 3 * g.P * sizeof(double2);
+    const size_t per_img = 3 * g.E * sizeof(double2);
     size_t c = ctx->ws_limit / nslots / per_img;
     if (c < 1) c = 1;
     if (c > (size_t)MAX_CHUNK) c = MAX_CHUNK;
@@ -163,7 +173,7 @@ int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
 int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, size_t nbits, size_t outbytes, size_t rawbytes) {
     int rc;
     const int nplanes = chunk * 3;
-    if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.P * sizeof(double2)))) return rc;
+    if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
     if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, CAND_CAP)))) return rc;
     if ((rc = ensure(ctx, S.medians, sizeof(double) * nplanes))) return rc;
     if ((rc = ensure(ctx, S.usable, sizeof(uint64_t) * chunk))) return rc;
@@ -197,19 +207,23 @@ PassArgs base_args(tfft_ctx* ctx, double2* spec, int nimg, const Geom& g, int ce
     a.center = center;
     a.in_rows = g.PH;
     a.out_rows = g.PH;
+    a.half = g.half;
+    a.ld = g.ld;
     return a;
 }
 
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
 int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
+    const double cols = (double)g.ld;  // columns the workspace keeps (PW, or PW/2+16 in half mode)
     a.img_in = d_img;
     a.axis = 0; a.log2n = g.lw; a.inverse = 0;
     a.in_rows = g.H;  // rows >= H are zero padding (S:395)
-    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
     a.img_in = nullptr;
     a.axis = 1; a.log2n = g.lh;  // in_rows stays H: the row pass left rows >= H unwritten (they are zero)
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * g.PW + (double)g.P)); CK(launch_fft_pass(L, a)); }
+    if (g.half) { a.PW = g.ld; a.half = 0; }  // the column pass just sees a plane of ld columns
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * cols + (double)g.PH * cols)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -217,13 +231,15 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
 // along image rows and can emit interleaved u8 directly.
 int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
+    const double cols = (double)g.ld;
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403): the column pass does not store them
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.P + (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
+    if (g.half) { a.PW = g.ld; a.half = 0; }
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.PH * cols + (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    a.PW = g.PW; a.half = g.half;
     a.axis = 0; a.log2n = g.lw;
     a.img_out = d_img;
-    a.out_rows = g.H;  // rows >= H are cropped away (S:399-403)
-    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * g.PW)); CK(launch_fft_pass(L, a)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -237,10 +253,10 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
     const int m = std::min(g.PH, g.PW);
-    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.P);
-      CK(launch_median_capacity(L, spec, nimg * 3, g.PH, g.PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
-    { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + 32.0 + 5.0));
-      CK(launch_embed(L, spec, nimg, g.PH, g.PW, d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.E);
+      CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
+      CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
     return inverse_images(ctx, L, spec, d_stego, nimg, g, center);
 }
 
@@ -253,10 +269,10 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
     if (rc) return rc;
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
-        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins));
     } else {
-        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins));
-        CK(launch_extract(L, spec, nimg, g.PH, g.PW, d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
+        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+        CK(launch_extract(L, spec, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
                           d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins));
     }
     return TFFT_OK;
@@ -330,6 +346,8 @@ int tfft_create(int device, tfft_ctx** out) {
     ctx->ws_limit = (size_t)((double)tot * 0.40);
     const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
     ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
+    const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
+    ctx->use_half = !(spc && !strcmp(spc, "full"));
     for (int i = 0; i < 2; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
@@ -350,7 +368,7 @@ void tfft_destroy(tfft_ctx* ctx) {
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
-    release(ctx->bins); release(ctx->jitter);
+    release(ctx->bins); release(ctx->jitter); release(ctx->full);
     prof_drain(ctx);
     for (cudaEvent_t ev : ctx->prof_pool) cudaEventDestroy(ev);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
@@ -396,7 +414,7 @@ int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, in
                          double* d_median, void* stream) {
     if (!ctx || !d_cover || !d_stego || n < 0 || (nbits && (!d_bins || !d_bits))) return TFFT_E_INVALID;
     Geom g;
-    int rc = make_geom(W, H, g);
+    int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
     CK(cudaSetDevice(ctx->device));
@@ -422,7 +440,7 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
                      uint8_t* stego, uint64_t* usable, double* median) {
     if (!ctx || !cover || !stego || n < 0 || (nbits && (!bins || !bits))) return TFFT_E_INVALID;
     Geom g;
-    int rc = make_geom(W, H, g);
+    int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
     if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
@@ -482,7 +500,7 @@ static int extract_dev_impl(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W,
                             uint8_t* d_out_payload, uint8_t* d_raw_bits, void* stream) {
     if (!ctx || !d_stego || n < 0 || (nbins && !d_bins) || nhdr > nbins) return TFFT_E_INVALID;
     Geom g;
-    int rc = make_geom(W, H, g);
+    int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
     CK(cudaSetDevice(ctx->device));
@@ -509,7 +527,7 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
                              uint8_t* out_payload, uint8_t* raw_bits) {
     if (!ctx || !stego || n < 0 || (nbins && !bins) || nhdr > nbins) return TFFT_E_INVALID;
     Geom g;
-    int rc = make_geom(W, H, g);
+    int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
     if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
@@ -591,18 +609,18 @@ int tfft_extract_frame(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
 int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center) {
     if (!ctx || !img || n <= 0) return TFFT_E_INVALID;
     Geom g;
-    int rc = make_geom(W, H, g);
+    int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    if ((size_t)n * 3 * g.P * sizeof(double2) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
+    if ((size_t)n * 3 * g.E * sizeof(double2) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
     Slot& S = ctx->slot[0];
     if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
     Launcher L = make_launcher(ctx, S.stream);
     if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (const uint8_t*)S.in.p, n, g, center))) return rc;
     CK(cudaStreamSynchronize(S.stream));
-    ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW;
+    ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay();
     return TFFT_OK;
 }
 
@@ -622,7 +640,7 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
     if ((rc = upload_bins(ctx, bins, nbins, jitter, S.stream))) return rc;
     Launcher L = make_launcher(ctx, S.stream);
     ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (16.0 + 4.0));
-    CK(launch_extract(L, (const double2*)S.spec.p, n, ctx->res_PH, ctx->res_PW, (const uint32_t*)ctx->bins.p, nbins, rep,
+    CK(launch_extract(L, (const double2*)S.spec.p, n, ctx->res_lay, (const uint32_t*)ctx->bins.p, nbins, rep,
                       jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
                       out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr));
     if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes, S.outbytes.p, (size_t)n * nb, cudaMemcpyDeviceToHost, S.stream));
@@ -636,7 +654,16 @@ int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int c
     int rc = tfft_forward_batch(ctx, img, 1, W, H, center);
     if (rc) return rc;
     Slot& S = ctx->slot[0];
-    CK(cudaMemcpy(out_c64, S.spec.p, 3 * (size_t)ctx->res_PH * ctx->res_PW * sizeof(double2), cudaMemcpyDeviceToHost));
+    const size_t full_bytes = 3 * (size_t)ctx->res_PH * ctx->res_PW * sizeof(double2);
+    if (ctx->res_lay.half) {  // expand the half-spectrum workspace for the caller
+        if ((rc = ensure(ctx, ctx->full, full_bytes))) return rc;
+        Launcher L = make_launcher(ctx, S.stream);
+        CK(launch_expand_half(L, (const double2*)S.spec.p, (double2*)ctx->full.p, 3, ctx->res_lay));
+        CK(cudaStreamSynchronize(S.stream));
+        CK(cudaMemcpy(out_c64, ctx->full.p, full_bytes, cudaMemcpyDeviceToHost));
+    } else {
+        CK(cudaMemcpy(out_c64, S.spec.p, full_bytes, cudaMemcpyDeviceToHost));
+    }
     return TFFT_OK;
 }
 
@@ -646,7 +673,7 @@ static int fft2d_planes(tfft_ctx* ctx, const Launcher& L, double2* d, int nplane
     memset(&a, 0, sizeof(a));
     a.spec = d; a.tw = ctx->d_tw; a.nplanes = nplanes;
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
-    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
+    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse; a.ld = PW;
     a.axis = 0; a.log2n = ilog2(PW);  // rows, then columns (S:361-365)
     { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)a.nplanes * 32.0 * (double)PH * PW); CK(launch_fft_pass(L, a)); }
     a.axis = 1; a.log2n = ilog2(PH);
@@ -679,7 +706,7 @@ int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data, int n, int PH, int PW, int 
     memset(&a, 0, sizeof(a));
     a.spec = (double2*)d_data; a.tw = ctx->d_tw; a.nplanes = n;
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
-    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse;
+    a.in_rows = PH; a.out_rows = PH; a.inverse = inverse; a.ld = PW;
     a.axis = axis; a.log2n = ilog2(axis == 0 ? PW : PH);
     { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)a.nplanes * 32.0 * (double)PH * PW); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
@@ -722,7 +749,7 @@ int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec, int n, int PH,
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
     const int m = std::min(PH, PW);
     ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)n * 3.0 * 16.0 * (double)PH * PW);
-    CK(launch_median_capacity(L, (const double2*)d_spec, n * 3, PH, PW, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
+    CK(launch_median_capacity(L, (const double2*)d_spec, n * 3, SpecLayout{PH, PW, PW, 0}, magmin, rmin * m, rmax * m, mw, d_median, d_usable));
     return TFFT_OK;
 }
 

@@ -192,6 +192,21 @@ __device__ __forceinline__ uint64_t mag_key(double2 z) {
     return (uint64_t)__double_as_longlong(hypot(z.x, z.y));  // std::abs(complex) S:406
 }
 
+// multiplicity of stored column x in the full PH x PW multiset (half layout: Hermitian mirror)
+__device__ __forceinline__ int col_weight(const SpecLayout& s, int x) {
+    if (!s.half) return 1;
+    const int h = s.PW >> 1;
+    return (x == 0 || x == h) ? 1 : (x < h ? 2 : 0);
+}
+// element (y,x) of the FULL spectrum
+__device__ __forceinline__ double2 spec_load(const double2* __restrict__ pl, const SpecLayout& s, int y, int x) {
+    if (!s.half || x <= (s.PW >> 1)) return pl[(size_t)y * s.ld + x];
+    const int cy = (s.PH - y) & (s.PH - 1), cx = s.PW - x;
+    double2 z = pl[(size_t)cy * s.ld + cx];
+    z.y = -z.y;
+    return z;
+}
+
 size_t median_work_bytes(int nplanes, uint32_t cand_cap) {
     size_t b = 0;
     b += (size_t)nplanes * RADIX * sizeof(uint32_t);
@@ -219,20 +234,23 @@ __global__ void median_init(MedianWork w, int nplanes, uint64_t P) {
 }
 
 // histogram of digit d over keys whose higher digits equal prefix; grid = (chunks, nplanes)
-__global__ void __launch_bounds__(512) median_hist(const double2* __restrict__ spec, uint64_t P, int d, MedianWork w, const int* gate) {
+__global__ void __launch_bounds__(512) median_hist(const double2* __restrict__ spec, SpecLayout lay, int d, MedianWork w, const int* gate) {
     __shared__ uint32_t sh[RADIX];
     if (gate && !*gate) return;  // degenerate-spectrum fallback not needed
     const int ip = blockIdx.y;
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const double2* pl = spec + (size_t)ip * P;
+    const uint64_t E = lay.plane_elems();
+    const double2* pl = spec + (size_t)ip * E;
     const int sft = key_shift(d), wid = key_width(d);
     const uint64_t prefix = w.prefix[ip];
     const int hi_sft = sft + wid;  // bits above this digit
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int wt = col_weight(lay, (int)(i % (uint64_t)lay.ld));
+        if (!wt) continue;
         const uint64_t k = mag_key(pl[i]);
         if (d == 0 || (k >> hi_sft) == (prefix >> hi_sft))
-            atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
+            atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], (unsigned)wt);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x)
@@ -349,29 +367,32 @@ __device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint
     return res;
 }
 
-__global__ void __launch_bounds__(256) median_sample(const double2* __restrict__ spec, uint64_t P, uint32_t S, uint64_t stride, MedianWork w) {
+__global__ void __launch_bounds__(256) median_sample(const double2* __restrict__ spec, SpecLayout lay, uint32_t S, uint64_t stride, MedianWork w) {
     const int ip = blockIdx.y;
-    const double2* pl = spec + (size_t)ip * P;
+    const double2* pl = spec + (size_t)ip * lay.plane_elems();
+    const int ncl = lay.half ? lay.PW >> 1 : lay.PW;  // logical columns sampled (weight-2 region of a half plane)
     // stratified pseudo-random positions: one element per stride block at a hashed offset (a fixed
     // offset would alias with the periodic leakage pattern that zero padding imprints on the spectrum)
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < S; j += gridDim.x * blockDim.x) {
         uint32_t h = (j + 0x9E3779B9u * (uint32_t)(ip + 1)) * 2654435761u;
         h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-        w.cand[(size_t)ip * w.cand_cap + j] = mag_key(pl[(uint64_t)j * stride + (uint64_t)(h % (uint32_t)stride)]);
+        const uint64_t li = (uint64_t)j * stride + (uint64_t)(h % (uint32_t)stride);
+        const uint64_t y = li / (uint64_t)ncl, x = li % (uint64_t)ncl;
+        w.cand[(size_t)ip * w.cand_cap + j] = mag_key(pl[y * (uint64_t)lay.ld + x]);
     }
 }
 
-// one CTA per plane.  exact != 0: the "sample" is the whole plane -> select the median directly.
-__global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, uint64_t P, int exact, Bracket* br, double* median) {
+// small planes (P <= cand_cap): no sampling, every element is a "member"
+__global__ void median_bracket_all(MedianWork w, int nplanes, Bracket* br) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip < nplanes) { br[ip].qlo = 0.0; br[ip].qhi = __longlong_as_double(0x7ff0000000000000LL); w.cand_n[ip] = 0; }
+}
+
+// one CTA per plane: sample quantiles 0.5 +- 6 sigma (sigma = 0.5/sqrt(S)) -> q-space bracket
+__global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, Bracket* br) {
     __shared__ SelectScratch sc;
     const int ip = blockIdx.x;
     const uint64_t* c = w.cand + (size_t)ip * w.cand_cap;
-    if (exact) {
-        const uint64_t k = select_rank(c, S, P / 2, &sc);
-        if (threadIdx.x == 0) { median[ip] = __longlong_as_double((long long)k); w.cand_n[ip] = 0; }
-        return;
-    }
-    // sample quantile 0.5 +- 6 sigma, sigma = 0.5/sqrt(S)
     const double delta = 3.0 / sqrt((double)S);
     long long rlo = (long long)floor((0.5 - delta) * S), rhi = (long long)ceil((0.5 + delta) * S);
     if (rlo < 0) rlo = 0;
@@ -388,10 +409,11 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
 
 constexpr int SCAN_UNROLL = 4;
 constexpr uint32_t SCAN_SBUF = 3072;  // members staged per CTA before one global reservation (24 KB)
-__global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ spec, uint64_t P, MedianWork w, const Bracket* __restrict__ br) {
+__global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ spec, SpecLayout lay, MedianWork w, const Bracket* __restrict__ br) {
     __shared__ uint64_t s_buf[SCAN_SBUF];
     __shared__ unsigned s_cnt, s_base, ws[16];
     const int ip = blockIdx.y;
+    const uint64_t P = lay.plane_elems();  // stored elements (weights restore the full multiset)
     const double2* pl = spec + (size_t)ip * P;
     const double qlo = br[ip].qlo, qhi = br[ip].qhi;
     uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
@@ -406,24 +428,27 @@ __global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ s
     (void)step;
     for (uint64_t base = lo; base < hi; base += (uint64_t)blockDim.x * SCAN_UNROLL) {
         double2 z[SCAN_UNROLL];
-        bool inb[SCAN_UNROLL];
+        int wt[SCAN_UNROLL];
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
             const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
-            inb[u] = i < hi;
-            z[u] = inb[u] ? pl[i] : make_double2(0.0, 0.0);
+            wt[u] = i < hi ? col_weight(lay, (int)(i % (uint64_t)lay.ld)) : 0;
+            z[u] = i < hi ? pl[i] : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
             const double q = fma(z[u].x, z[u].x, z[u].y * z[u].y);
-            const bool member = inb[u] && q >= qlo && q <= qhi;
-            if (inb[u] && q < qlo) below++;
-            const unsigned m = __ballot_sync(0xffffffffu, member);
-            if (m) {
+            const bool member = wt[u] && q >= qlo && q <= qhi;
+            if (q < qlo) below += wt[u];
+            // a weight-2 member (a bin and its Hermitian mirror) enters the list twice
+            for (int rep = 0; rep < 2; rep++) {
+                const bool put = member && wt[u] > rep;
+                const unsigned m = __ballot_sync(0xffffffffu, put);
+                if (!m) break;
                 unsigned b0 = 0;
                 if (lane == 0) b0 = atomicAdd(&s_cnt, (unsigned)__popc(m));
                 b0 = __shfl_sync(0xffffffffu, b0, 0);
-                if (member) {
+                if (put) {
                     const unsigned slot = b0 + __popc(m & ((1u << lane) - 1));
                     const uint64_t key = mag_key(z[u]);
                     if (slot < SCAN_SBUF) s_buf[slot] = key;
@@ -451,12 +476,12 @@ __global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ s
 }
 
 // one CTA per plane: exact rank among the members, or raise the fallback flag
-__global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, double* median, int* flag) {
+__global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, double* median, int* flag, uint32_t guard) {
     __shared__ SelectScratch sc;
     const int ip = blockIdx.x;
     const uint32_t n = w.cand_n[ip];
     const uint64_t below = w.counts[ip], rank = P / 2;
-    const bool ok = n <= w.cand_cap && rank >= below + RANK_GUARD && rank + RANK_GUARD < below + n;
+    const bool ok = n <= w.cand_cap && rank >= below + guard && rank + guard < below + n;
     if (!ok) {
         if (threadIdx.x == 0) *flag = 1;
         return;
@@ -468,12 +493,13 @@ __global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P,
 // Capacity count (S:999-1007): annulus bins in index space (radius from bin (0,0), scaled by
 // min(PH,PW)), off the axes (on_axis S:698), |F| >= magmin*median, conjugate distinct.
 // Only the quarter-disc y,x <= rhi can satisfy the radius test, so only that box is scanned.
-__global__ void __launch_bounds__(256) capacity_count(const double2* __restrict__ spec, int PH, int PW, int ymax, int xmax,
+__global__ void __launch_bounds__(256) capacity_count(const double2* __restrict__ spec, SpecLayout lay, int ymax, int xmax,
                                                       double rlo, double rhi, double magmin,
                                                       const double* __restrict__ median, uint64_t* counts) {
     const int ip = blockIdx.y;
+    const int PH = lay.PH, PW = lay.PW;
     const double thr = magmin * median[ip];
-    const double2* pl = spec + (size_t)ip * PH * PW;
+    const double2* pl = spec + (size_t)ip * lay.plane_elems();
     const long long box = (long long)(ymax + 1) * (xmax + 1);
     unsigned local = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < box; i += (long long)gridDim.x * blockDim.x) {
@@ -481,7 +507,7 @@ __global__ void __launch_bounds__(256) capacity_count(const double2* __restrict_
         if (y == 0 || x == 0 || y == PH / 2 || x == PW / 2) continue;  // PH, PW are even powers of two
         const double r = sqrt((double)((long long)y * y + (long long)x * x));  // == hypot for exact integer sums
         if (r < rlo || r > rhi) continue;
-        const double2 z = pl[(size_t)y * PW + x];
+        const double2 z = spec_load(pl, lay, y, x);
         if (hypot(z.x, z.y) < thr) continue;
         local++;  // conjugate (PH-y, PW-x) != (y,x) is implied by the axis test
     }
@@ -501,11 +527,13 @@ __global__ void capacity_finish(const uint64_t* counts, uint64_t* usable, int ni
     if (i < nimg) usable[i] = counts[3 * i] / 2 + counts[3 * i + 1] / 2 + counts[3 * i + 2] / 2;  // S:1006, S:1008
 }
 
-cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, int PH, int PW,
+cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
                                    double* d_median, uint64_t* d_usable) {
-    const uint64_t P = (uint64_t)PH * PW;
-    const int chunks = (int)((P + 512ull * 16 - 1) / (512ull * 16));
+    const int PH = lay.PH, PW = lay.PW;
+    const uint64_t P = (uint64_t)PH * PW;        // size of the full multiset (ranks refer to it)
+    const uint64_t E = lay.plane_elems();        // stored elements per plane
+    const int chunks = (int)((E + 512ull * 16 - 1) / (512ull * 16));
     const dim3 grid((unsigned)(chunks > 592 ? 592 : chunks), (unsigned)nplanes);
     median_init<<<(nplanes * RADIX + 255) / 256, 256, 0, L.stream>>>(w, nplanes, P);
     TFFT_LAUNCH_CHECK(L);
@@ -513,23 +541,29 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     Bracket* br = (Bracket*)w.prefix2;
     cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), L.stream);
     if (e != cudaSuccess) return e;
-    const bool exact = P <= (uint64_t)w.cand_cap && P <= (uint64_t)SAMPLE_MAX;
-    const uint32_t S = exact ? (uint32_t)P : (SAMPLE_MAX < w.cand_cap ? SAMPLE_MAX : w.cand_cap);
-    const uint64_t stride = exact ? 1 : P / S;
-    median_sample<<<dim3((S + 255) / 256 > 256 ? 256 : (S + 255) / 256, (unsigned)nplanes), 256, 0, L.stream>>>(spec, P, S, stride, w);
-    TFFT_LAUNCH_CHECK(L);
-    median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, P, exact ? 1 : 0, br, d_median);
-    TFFT_LAUNCH_CHECK(L);
-    if (!exact) {
-        median_scan<<<grid, 512, 0, L.stream>>>(spec, P, w, br);
+    const bool all = P <= (uint64_t)w.cand_cap && P <= (uint64_t)SAMPLE_MAX;  // small plane: everything is a member
+    if (all) {
+        median_bracket_all<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, nplanes, br);
         TFFT_LAUNCH_CHECK(L);
-        median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, d_median, d_flag);
+    } else {
+        const uint64_t logical = lay.half ? P / 2 : P;
+        const uint32_t S = SAMPLE_MAX < w.cand_cap ? SAMPLE_MAX : w.cand_cap;
+        const uint64_t stride = logical / S;
+        median_sample<<<dim3((S + 255) / 256 > 256 ? 256 : (S + 255) / 256, (unsigned)nplanes), 256, 0, L.stream>>>(spec, lay, S, stride, w);
         TFFT_LAUNCH_CHECK(L);
-        // Fallback, decided on the device (no host sync): the generic radix passes are gated by the
-        // flag and exit immediately in the normal case.
+        median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, br);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    median_scan<<<grid, 512, 0, L.stream>>>(spec, lay, w, br);
+    TFFT_LAUNCH_CHECK(L);
+    median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, d_median, d_flag, all ? 0u : RANK_GUARD);
+    TFFT_LAUNCH_CHECK(L);
+    // Fallback, decided on the device (no host sync): the generic radix passes are gated by the
+    // flag and exit immediately in the normal case.
+    {
         const dim3 fgrid(8, (unsigned)nplanes);  // rarely does real work: keep the gated launches cheap
         for (int d = 0; d < NUM_DIGITS; d++) {
-            median_hist<<<fgrid, 512, 0, L.stream>>>(spec, P, d, w, d_flag);
+            median_hist<<<fgrid, 512, 0, L.stream>>>(spec, lay, d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
             median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
@@ -540,8 +574,6 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
     if (e != cudaSuccess) return e;
     if (d_usable) {
-        const int m = PH < PW ? PH : PW;
-        (void)m;
         int ymax = (int)floor(rhi), xmax = (int)floor(rhi);
         if (ymax > PH - 1) ymax = PH - 1;
         if (xmax > PW - 1) xmax = PW - 1;
@@ -551,7 +583,7 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         int cb = (int)((box + 256 * 8 - 1) / (256 * 8));
         if (cb > 1184) cb = 1184;
         if (cb < 1) cb = 1;
-        capacity_count<<<dim3((unsigned)cb, (unsigned)nplanes), 256, 0, L.stream>>>(spec, PH, PW, ymax, xmax, rlo, rhi, magmin, d_median, w.counts);
+        capacity_count<<<dim3((unsigned)cb, (unsigned)nplanes), 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts);
         TFFT_LAUNCH_CHECK(L);
         capacity_finish<<<(nplanes / 3 + 255) / 256, 256, 0, L.stream>>>(w.counts, d_usable, nplanes / 3);
         TFFT_LAUNCH_CHECK(L);
@@ -564,7 +596,7 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
 // +-alpha (+ jitter), conjugate bin mirrored so the plane stays real.  Bins are unique and
 // never alias a conjugate (Turtle::mark_here S:805-809), so the scatter is conflict-free.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) embed_scatter(double2* spec, int PH, int PW, const uint32_t* __restrict__ bins,
+__global__ void __launch_bounds__(256) embed_scatter(double2* spec, SpecLayout lay, const uint32_t* __restrict__ bins,
                                                      const uint8_t* __restrict__ bits, size_t nbits,
                                                      const double* __restrict__ jitter, double alpha,
                                                      double cos_a, double sin_a, const uint64_t* __restrict__ usable) {
@@ -572,12 +604,17 @@ __global__ void __launch_bounds__(256) embed_scatter(double2* spec, int PH, int 
     if (usable && usable[img] < (uint64_t)nbits) return;  // S:1009: over capacity -> image untouched
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbits) return;
+    const int PH = lay.PH, PW = lay.PW;
     const uint32_t b = bins[i];
     const int p = (int)(b >> 30);
     const uint32_t lin = b & 0x3FFFFFFFu;
     const int y = (int)(lin / (uint32_t)PW), x = (int)(lin % (uint32_t)PW);
-    double2* pl = spec + (size_t)(img * 3 + p) * PH * PW;
-    const double2 z = pl[lin];
+    const int cy = (PH - y) & (PH - 1), cx = (PW - x) & (PW - 1);  // conj_idx S:370-372 (powers of two)
+    double2* pl = spec + (size_t)(img * 3 + p) * lay.plane_elems();
+    // which of (bin, mirror) live in the workspace: full layout both; half layout the one(s) with x <= PW/2
+    const bool have_bin = !lay.half || x <= (PW >> 1);
+    const bool have_mir = !lay.half || cx <= (PW >> 1);
+    const double2 z = have_bin ? pl[(size_t)y * lay.ld + x] : pl[(size_t)cy * lay.ld + cx];  // |conj| == |z|
     const double mag = fmax(1e-12, hypot(z.x, z.y));
     const int bit = bits[(size_t)img * nbits + i];
     double c, s;
@@ -589,21 +626,20 @@ __global__ void __launch_bounds__(256) embed_scatter(double2* spec, int PH, int 
         s = bit ? sin_a : -sin_a;
     }
     const double2 nv = make_double2(mag * c, mag * s);  // std::polar(mag, theta)
-    const int cy = (PH - y) % PH, cx = (PW - x) % PW;   // conj_idx S:370-372
     if (cy == y && cx == x) {
-        pl[lin] = make_double2(mag, 0.0);  // S:727
+        pl[(size_t)y * lay.ld + x] = make_double2(mag, 0.0);  // S:727
     } else {
-        pl[lin] = nv;
-        pl[(size_t)cy * PW + cx] = make_double2(nv.x, -nv.y);
+        if (have_bin) pl[(size_t)y * lay.ld + x] = nv;
+        if (have_mir) pl[(size_t)cy * lay.ld + cx] = make_double2(nv.x, -nv.y);
     }
 }
 
-cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, int PH, int PW,
+cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,
                          const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
                          double alpha, double cos_a, double sin_a, const uint64_t* usable) {
     if (nbits == 0 || nimg == 0) return cudaSuccess;
     dim3 grid((unsigned)((nbits + 255) / 256), (unsigned)nimg);
-    embed_scatter<<<grid, 256, 0, L.stream>>>(spec, PH, PW, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable);
+    embed_scatter<<<grid, 256, 0, L.stream>>>(spec, lay, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable);
     TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }
@@ -622,11 +658,12 @@ __device__ __forceinline__ int read_bit(double2 z, double alpha, double jit) {
     const double th = atan2(z.y, z.x);
     return ang_diff(th, jit + alpha) <= ang_diff(th, jit - alpha) ? 1 : 0;
 }
-__device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, int img, size_t P, uint32_t b) {
-    return spec[(size_t)(img * 3 + (int)(b >> 30)) * P + (b & 0x3FFFFFFFu)];
+__device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, int img, const SpecLayout& lay, uint32_t b) {
+    const uint32_t lin = b & 0x3FFFFFFFu;
+    return spec_load(spec + (size_t)(img * 3 + (int)(b >> 30)) * lay.plane_elems(), lay, (int)(lin / (uint32_t)lay.PW), (int)(lin % (uint32_t)lay.PW));
 }
 
-__global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ spec, size_t P, const uint32_t* __restrict__ bins,
+__global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ spec, SpecLayout P, const uint32_t* __restrict__ bins,
                                                    size_t nbins, const double* __restrict__ jitter, double alpha,
                                                    uint8_t* raw_bits, size_t raw_stride) {
     const int img = blockIdx.y;
@@ -636,7 +673,7 @@ __global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ s
 }
 
 // one thread per decoded bit; a warp packs 32 decoded bits into 4 bytes with a ballot
-__global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ spec, size_t P, const uint32_t* __restrict__ bins,
+__global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ spec, SpecLayout P, const uint32_t* __restrict__ bins,
                                                     size_t ndec, int rep, const double* __restrict__ jitter, double alpha,
                                                     uint8_t* out_bytes, size_t nbytes) {
     const int img = blockIdx.y;
@@ -656,11 +693,10 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
     if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
 }
 
-cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
+cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout P,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
                            uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride) {
     if (nimg == 0) return cudaSuccess;
-    const size_t P = (size_t)PH * PW;
     if (raw_bits && nbins) {
         extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits, raw_stride ? raw_stride : nbins);
         TFFT_LAUNCH_CHECK(L);
@@ -671,6 +707,21 @@ cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int
         extract_vote<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, ndec, rep, jitter, alpha, out_bytes, nbytes);
         TFFT_LAUNCH_CHECK(L);
     }
+    return cudaSuccess;
+}
+
+
+// full[y][x] from a half-spectrum workspace (parity hook only)
+__global__ void expand_half(const double2* __restrict__ hs, double2* __restrict__ fs, SpecLayout lay) {
+    const int ip = blockIdx.y;
+    const size_t P = (size_t)lay.PH * lay.PW;
+    const double2* pl = hs + (size_t)ip * lay.plane_elems();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (size_t)gridDim.x * blockDim.x)
+        fs[(size_t)ip * P + i] = spec_load(pl, lay, (int)(i / lay.PW), (int)(i % lay.PW));
+}
+cudaError_t launch_expand_half(const Launcher& L, const double2* half_spec, double2* full_spec, int nplanes, SpecLayout lay) {
+    expand_half<<<dim3(1024, (unsigned)nplanes), 256, 0, L.stream>>>(half_spec, full_spec, lay);
+    TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }
 

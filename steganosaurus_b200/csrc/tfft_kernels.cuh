@@ -32,6 +32,19 @@ struct PassArgs {
     int in_rows;  // plane rows y >= in_rows are all-zero on input and are NOT read
                   //   (axis 0: such pencils are skipped; axis 1: those elements are zero-filled)
     int out_rows; // plane rows y >= out_rows are not needed downstream and are NOT written
+    // Half-spectrum mode (real planes): the workspace keeps columns 0..PW/2 with row stride ld =
+    // PW/2 + 16.  u8 passes get half = 1 (PW = full width, ld = stride); column passes simply see a
+    // plane of PW := ld columns.
+    int half;
+    int ld;
+};
+
+// How a plane's spectrum is stored.  full: [PH][PW], ld = PW.  half (real planes, Hermitian):
+// columns 0..PW/2 only, row stride ld = PW/2 + 16 (pad columns are zero); element (y,x) with
+// x > PW/2 is conj of the stored element ((PH-y)%PH, PW-x).
+struct SpecLayout {
+    int PH, PW, ld, half;
+    __host__ __device__ size_t plane_elems() const { return (size_t)PH * ld; }
 };
 
 struct Launcher {
@@ -59,18 +72,21 @@ struct MedianWork {
 size_t median_work_bytes(int nplanes, uint32_t cand_cap);
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);
 // d_median: [nplanes]; d_usable: [nplanes/3] (sum over the 3 planes of count/2)
-cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, int PH, int PW,
+cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
                                    double* d_median, uint64_t* d_usable);
 
 // ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
-cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, int PH, int PW,
+cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,
                          const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
                          double alpha, double cos_a, double sin_a, const uint64_t* usable);
 
 // ---- extract gather + vote (read_bit_from_bin S:734-746, rep3/7 S:468/S:501, pack S:447) --
-cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, int PH, int PW,
+cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout lay,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
                            uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+
+// full[y][x] from the half layout (parity hook tfft_forward_spectrum)
+cudaError_t launch_expand_half(const Launcher& L, const double2* half_spec, double2* full_spec, int nplanes, SpecLayout lay);
 
 }  // namespace tfft

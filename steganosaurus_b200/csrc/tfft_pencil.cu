@@ -620,6 +620,239 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv(U8A
     }
 }
 
+// ==========================================================================================
+// Real-input symmetry: half-spectrum passes.
+// A real plane's spectrum is Hermitian, F[y][x] = conj(F[(PH-y)%PH][(PW-x)%PW]), so only columns
+// x = 0 .. PW/2 are kept (row stride ld = PW/2 + 16; the 15 pad columns are zero).  Two image rows
+// share one complex FFT: z = row_a + i*row_b.  Halves the column passes, the workspace, the median
+// scan and the row-pass FP64 work.  Results are the same within rounding (the reference's spectrum
+// is Hermitian to ~1e-12, and S:401 keeps only the real part of the inverse).
+// ==========================================================================================
+struct R2CArgs {
+    double2* spec;      // [nplanes][PH][ld]
+    const double2* tw;
+    const uint8_t* img_in;
+    uint8_t* img_out;
+    long long nitems;   // nimg * ceil(H/2) row pairs
+    int W, H, PW, PH, ld, center;
+};
+
+// ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
+template <int LOG2N, int UNITS>
+__global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c(R2CArgs a) {
+    using G = Geo<LOG2N, 1>;
+    constexpr int N = G::N, NH = N / 2;
+    constexpr size_t UB = (size_t)2 * N * 3 + 32;  // aligned span of two adjacent RGB rows
+    constexpr size_t UNIT_BYTES = G::L_BYTES + 2 * UB;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
+    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    double2* L = (double2*)base;
+    unsigned char* U[2] = {base + G::L_BYTES, base + G::L_BYTES + UB};
+    const int bar_id = 1 + unit;
+    const long long stride = (long long)gridDim.x * UNITS;
+    long long item = (long long)blockIdx.x * UNITS + unit;
+    const int HP = (a.H + 1) / 2;  // row pairs per image
+    const size_t row_bytes = (size_t)a.W * 3;
+    const uintptr_t img_base = (uintptr_t)a.img_in;
+    ThreadTw<+1, LOG2N, 1> ttw;
+    ttw.load(a.tw, tt);
+
+    auto pair_start = [&](long long it) -> uintptr_t {
+        const long long img = it / HP;
+        const int y0 = 2 * (int)(it % HP);
+        return img_base + ((size_t)img * a.H + y0) * row_bytes;
+    };
+    auto pair_rows = [&](long long it) -> int { return (2 * (int)(it % HP) + 1 < a.H) ? 2 : 1; };
+    auto issue_rows = [&](long long it, unsigned char* dst) {
+        const uintptr_t start = pair_start(it);
+        const size_t nbytes = row_bytes * pair_rows(it);
+        const uintptr_t a0 = start & ~(uintptr_t)15;
+        const int nchunks = (int)((start + nbytes - a0 + 15) >> 4);
+        const uintptr_t end = start + nbytes;  // never read past the pair (the next bytes may not exist)
+        for (int i = tt; i < nchunks; i += G::UT) {
+            const uintptr_t src = a0 + (size_t)i * 16;
+            long long avail = (long long)(end - src);
+            int nb = avail >= 16 ? 16 : (avail > 0 ? (int)avail : 0);
+            cp_async16(dst + (size_t)i * 16, (const void*)(nb ? src : img_base), nb);
+        }
+        cp_async_commit();
+    };
+
+    if (unit & 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < STAGGER_CYCLES) {}
+    }
+    int buf = 0;
+    if (item < a.nitems) issue_rows(item, U[0]);
+    for (; item < a.nitems; item += stride, buf ^= 1) {
+        cp_async_wait_all();
+        unit_bar(bar_id, G::UT);
+        if (item + stride < a.nitems) issue_rows(item + stride, U[buf ^ 1]);
+        const long long img = item / HP;
+        const int y0 = 2 * (int)(item % HP);
+        const int nrows = pair_rows(item);
+        const uint8_t* r0 = U[buf] + (pair_start(item) & 15);
+        const uint8_t* r1 = r0 + row_bytes;
+        for (int ch = 0; ch < 3; ch++) {
+            // ---- stage 1 on z = row0 + i*row1 (plane split, centre sign, zero pad fused; S:383-398)
+#pragma unroll
+            for (int j = 0; j < G::J1; j++) {
+                const int m = tt + j * G::TP;
+                double2 x[G::R1];
+#pragma unroll
+                for (int n = 0; n < G::R1; n++) {
+                    const int xc = n * 256 + m;
+                    double v0 = 0.0, v1 = 0.0;
+                    if (xc < a.W) {
+                        v0 = (double)r0[xc * 3 + ch];
+                        if (nrows == 2) v1 = (double)r1[xc * 3 + ch];
+                        if (a.center) {  // apply_center S:392: (-1)^(x+y)
+                            if ((xc + y0) & 1) v0 = -v0; else v1 = -v1;
+                        }
+                    }
+                    x[n] = make_double2(v0, v1);
+                }
+                dft<+1, G::R1>(x);
+                double2 w1 = a.tw[(size_t)m << (TW_LOG2 - LOG2N)];
+                twiddle<G::R1>(x, w1);
+#pragma unroll
+                for (int k = 0; k < G::R1; k++) L[k * 256 + m] = x[oidx<G::R1>(k)];
+            }
+            unit_bar(bar_id, G::UT);
+            double2 x[16];
+            stage2_load<LOG2N, 1>(L, tt, 0, x);
+            unit_bar(bar_id, G::UT);
+            stage23_inplace<+1, LOG2N>(L, tt, ttw.s2v(), x, bar_id);  // x[oidx(k3)] = Z[tt + TP*k3]
+            unit_bar(bar_id, G::UT);                                  // all reads of L done
+            // ---- split Z into the spectra of the two real rows: partners Z[N-k] through L
+#pragma unroll
+            for (int k3 = 8; k3 < 16; k3++) L[tt + G::TP * (k3 - 8)] = x[oidx<16>(k3)];  // Z[N/2 + j] at L[j]
+            unit_bar(bar_id, G::UT);
+            double2* out0 = a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
+            double2* out1 = out0 + a.ld;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) {
+                const int k = tt + G::TP * k3;
+                const double2 z = x[oidx<16>(k3)];
+                const double2 zn = (k == 0) ? z : L[NH - k];  // Z[N-k] = L[(N-k) - N/2]
+                out0[k] = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));            // (Z[k] + conj Z[N-k]) / 2
+                if (nrows == 2) out1[k] = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));  // (Z[k] - conj Z[N-k]) / 2i
+            }
+            if (tt < 16) {  // Nyquist column (real) and the zero pad columns N/2+1 .. N/2+15
+                const double2 z8 = x[oidx<16>(8)];
+                out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
+                if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
+            }
+            unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
+        }
+    }
+}
+
+// ---- inverse: 2 x 3 half-spectrum rows -> two u8 rows (C2R + scale/crop/centre/round/clamp) ----
+template <int LOG2N, int UNITS>
+__global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r(R2CArgs a) {
+    using G = Geo<LOG2N, 1>;
+    constexpr int N = G::N, NH = N / 2, HL = NH + 1;  // HL entries per half row
+    constexpr size_t LB = (size_t)(N + 2) * 16 + 32;  // landing: A half then B half; exchange 1 reuses [0,N)
+    constexpr size_t UNIT_BYTES = LB + G::X_BYTES;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
+    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    double2* L = (double2*)base;
+    double* X = (double*)(base + LB);
+    const int bar_id = 1 + unit;
+    const long long stride = (long long)gridDim.x * UNITS;
+    long long item = (long long)blockIdx.x * UNITS + unit;
+    const int HP = (a.H + 1) / 2;
+    const size_t row_bytes = (size_t)a.W * 3;
+    const double scale = 1.0 / (double)N;  // S:357
+    ThreadTw<-1, LOG2N, 1> ttw;
+    ttw.load(a.tw, tt);
+
+    auto src_rows = [&](long long it, int ch) -> const double2* {
+        const long long img = it / HP;
+        const int y0 = 2 * (int)(it % HP);
+        return a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
+    };
+    auto issue_loads = [&](long long it, int ch) {
+        const double2* A = src_rows(it, ch);
+        const bool two = 2 * (int)(it % HP) + 1 < a.H;  // odd-H tail: the second row is absent (zero)
+        for (int e = tt; e < 2 * HL; e += G::UT) {
+            const bool isB = e >= HL;
+            const double2* src = isB ? A + a.ld + (e - HL) : A + e;
+            const bool valid = !isB || two;
+            cp_async16(&L[e], valid ? (const void*)src : (const void*)a.spec, valid ? 16 : 0);
+        }
+        cp_async_commit();
+    };
+
+    if (unit & 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < STAGGER_CYCLES) {}
+    }
+    if (item < a.nitems) issue_loads(item, 0);
+    for (; item < a.nitems; item += stride) {
+        const long long img = item / HP;
+        const int y0 = 2 * (int)(item % HP);
+        const bool two = y0 + 1 < a.H;
+        uint8_t* o0 = a.img_out + ((size_t)img * a.H + y0) * row_bytes;
+        uint8_t* o1 = o0 + row_bytes;
+        for (int ch = 0; ch < 3; ch++) {
+            cp_async_wait_all();
+            unit_bar(bar_id, G::UT);
+            // ---- gather Z[k] = A[k] + i B[k] (k <= N/2) or conj(A[N-k]) + i conj(B[N-k]) (k > N/2)
+            double2 x[16];
+#pragma unroll
+            for (int j = 0; j < G::J1; j++) {
+                const int m = tt + j * G::TP;
+#pragma unroll
+                for (int n = 0; n < G::R1; n++) {
+                    const int k = n * 256 + m;
+                    if (k <= NH) {
+                        const double2 A = L[k], B = L[HL + k];
+                        x[j * G::R1 + n] = make_double2(A.x - B.y, A.y + B.x);
+                    } else {
+                        const double2 A = L[N - k], B = L[HL + N - k];
+                        x[j * G::R1 + n] = make_double2(A.x + B.y, B.x - A.y);
+                    }
+                }
+            }
+            unit_bar(bar_id, G::UT);  // every thread has its inputs: exchange 1 may overwrite the landing area
+#pragma unroll
+            for (int j = 0; j < G::J1; j++) {
+                const int m = tt + j * G::TP;
+                double2* xj = x + j * G::R1;
+                dft<-1, G::R1>(xj);
+                double2 w1 = a.tw[(size_t)m << (TW_LOG2 - LOG2N)];
+                w1.y = -w1.y;
+                twiddle<G::R1>(xj, w1);
+#pragma unroll
+                for (int k = 0; k < G::R1; k++) L[k * 256 + m] = xj[oidx<G::R1>(k)];
+            }
+            unit_bar(bar_id, G::UT);
+            stage2_load<LOG2N, 1>(L, tt, 0, x);
+            unit_bar(bar_id, G::UT);  // L is free: prefetch the next plane / the next item's first plane
+            if (ch < 2) issue_loads(item, ch + 1);
+            else if (item + stride < a.nitems) issue_loads(item + stride, 0);
+            stage23<-1, LOG2N, 1>(X, tt, 0, ttw.s2v(), x, bar_id);
+            // ---- epilogue (ifft_crop S:399, apply_center S:1102, from_planes_u8 S:387): Re -> row y0, Im -> row y0+1
+#pragma unroll
+            for (int k3 = 0; k3 < 16; k3++) {
+                const int k = tt + G::TP * k3;
+                if (k < a.W) {
+                    double v0 = x[oidx<16>(k3)].x * scale, v1 = x[oidx<16>(k3)].y * scale;
+                    if (a.center) {
+                        if ((k + y0) & 1) v0 = -v0; else v1 = -v1;
+                    }
+                    o0[(size_t)k * 3 + ch] = clamp8(v0);
+                    if (two) o1[(size_t)k * 3 + ch] = clamp8(v1);
+                }
+            }
+        }
+    }
+}
+
 }  // namespace pk
 
 // ------------------------------------------------------------------------------------------
@@ -726,6 +959,28 @@ cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
     return cudaGetLastError();
 }
 
+template <int LOG2N, int UNITS, bool INV>
+cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
+    using G = pk::Geo<LOG2N, 1>;
+    pk::R2CArgs a;
+    a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
+    a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
+    a.nitems = (long long)(p.nplanes / 3) * ((p.H + 1) / 2);
+    const size_t smem = (INV ? ((size_t)(G::N + 2) * 16 + 32 + G::X_BYTES) : (G::L_BYTES + 2 * ((size_t)2 * G::N * 3 + 32))) * UNITS;
+    cudaError_t e;
+    if constexpr (INV) {
+        auto kern = pk::pencil_u8_inv_c2r<LOG2N, UNITS>;
+        if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+    } else {
+        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS>;
+        if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
+        kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+    }
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
 // per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB
 template <int LOG2N>
 struct Cfg;
@@ -737,6 +992,8 @@ template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, CO
 template <int LOG2N>
 cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     using C = Cfg<LOG2N>;
+    if (p.half && p.img_in) return run_r2c<LOG2N, C::U8F_UNITS, false>(L, p);
+    if (p.half && p.img_out) return run_r2c<LOG2N, C::U8I_UNITS, true>(L, p);
     if (p.img_in) return run_u8<LOG2N, C::U8F_UNITS, false>(L, p);
     if (p.img_out) return run_u8<LOG2N, C::U8I_UNITS, true>(L, p);
     if (p.axis == 0)
