@@ -33,6 +33,8 @@ struct Slot {
 
 }  // namespace
 
+constexpr int NSLOT = 3;  // host pipeline depth: H2D of chunk i+1, kernels of chunk i, D2H of chunk i-1 overlap
+
 struct tfft_ctx {
     int device = 0;
     int sm_count = 0;
@@ -40,7 +42,7 @@ struct tfft_ctx {
     size_t total_mem = 0;
     size_t ws_limit = 0;
     double2* d_tw = nullptr;
-    Slot slot[2];
+    Slot slot[NSLOT];
     DevBuf bins, jitter;
     uint64_t launches = 0;
     int fft_impl = 1;
@@ -348,7 +350,7 @@ int tfft_create(int device, tfft_ctx** out) {
     ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
     if (e == cudaSuccess) e = build_twiddles(ctx->d_tw, ctx->slot[0].stream);
@@ -361,7 +363,7 @@ void tfft_destroy(tfft_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
         release(S.spec); release(S.in); release(S.out); release(S.bits); release(S.med);
         release(S.medians); release(S.usable); release(S.outbytes); release(S.raw);
@@ -446,8 +448,8 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = std::min(chunk_for(ctx, g, n, 2), HOST_CHUNK);
-    const int nslots = (n > chunk) ? 2 : 1;
+    const int chunk = std::min(chunk_for(ctx, g, n, NSLOT), HOST_CHUNK);
+    const int nslots = std::min(NSLOT, (n + chunk - 1) / chunk);
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
@@ -455,7 +457,8 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_stage(ctx, ctx->slot[s], stage_bytes))) return rc;
     bool over = false;
-    int pend_i0[2] = {-1, -1}, pend_m[2] = {0, 0};
+    int pend_i0[NSLOT], pend_m[NSLOT];
+    for (int s = 0; s < NSLOT; s++) { pend_i0[s] = -1; pend_m[s] = 0; }
     auto drain = [&](int s) -> int {  // wait for the slot's chunk and hand its small results to the caller
         if (pend_i0[s] < 0) return TFFT_OK;
         Slot& S = ctx->slot[s];
@@ -472,7 +475,7 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     };
     int ci = 0;
     for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
-        const int sl = ci & 1;
+        const int sl = ci % nslots;
         Slot& S = ctx->slot[sl];
         const int m = std::min(chunk, n - i0);
         cudaStream_t st = S.stream;
@@ -489,8 +492,8 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
         CK(cudaMemcpyAsync(S.h_stage + (size_t)chunk * sizeof(uint64_t), S.medians.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
         pend_i0[sl] = i0; pend_m[sl] = m;
     }
-    for (int s = 0; s < 2; s++)
-        if ((rc = drain(s))) return rc;
+    for (int k = 0; k < nslots; k++)  // oldest first
+        if ((rc = drain((ci + k) % nslots))) return rc;
     return over ? TFFT_E_CAPACITY : TFFT_OK;
 }
 
@@ -533,8 +536,8 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = std::min(chunk_for(ctx, g, n, 2), HOST_CHUNK);
-    const int nslots = (n > chunk) ? 2 : 1;
+    const int chunk = std::min(chunk_for(ctx, g, n, NSLOT), HOST_CHUNK);
+    const int nslots = std::min(NSLOT, (n + chunk - 1) / chunk);
     const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
     const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
     // header bytes and payload bytes share one device buffer per slot: [chunk][nb] then [chunk][nbp]
@@ -544,7 +547,8 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     const size_t per_img = (out ? nb : 0) + (out_payload ? nbp : 0);
     for (int s = 0; s < nslots; s++)
         if (per_img && (rc = ensure_stage(ctx, ctx->slot[s], (size_t)chunk * per_img))) return rc;
-    int pend_i0[2] = {-1, -1}, pend_m[2] = {0, 0};
+    int pend_i0[NSLOT], pend_m[NSLOT];
+    for (int s = 0; s < NSLOT; s++) { pend_i0[s] = -1; pend_m[s] = 0; }
     auto drain = [&](int s) -> int {
         if (pend_i0[s] < 0) return TFFT_OK;
         Slot& S = ctx->slot[s];
@@ -556,7 +560,7 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     };
     int ci = 0;
     for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
-        const int sl = ci & 1;
+        const int sl = ci % nslots;
         Slot& S = ctx->slot[sl];
         const int m = std::min(chunk, n - i0);
         cudaStream_t st = S.stream;
@@ -574,8 +578,8 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
         if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits + (size_t)i0 * nbins, S.raw.p, (size_t)m * nbins, cudaMemcpyDeviceToHost, st));
         pend_i0[sl] = i0; pend_m[sl] = m;
     }
-    for (int s = 0; s < 2; s++)
-        if ((rc = drain(s))) return rc;
+    for (int k = 0; k < nslots; k++)
+        if ((rc = drain((ci + k) % nslots))) return rc;
     return TFFT_OK;
 }
 

@@ -388,21 +388,52 @@ __global__ void median_bracket_all(MedianWork w, int nplanes, Bracket* br) {
     if (ip < nplanes) { br[ip].qlo = 0.0; br[ip].qhi = __longlong_as_double(0x7ff0000000000000LL); w.cand_n[ip] = 0; }
 }
 
-// one CTA per plane: sample quantiles 0.5 +- 6 sigma (sigma = 0.5/sqrt(S)) -> q-space bracket
+// one CTA per plane: sample quantiles 0.5 +- 6 sigma (sigma = 0.5/sqrt(S)) -> q-space bracket.
+// The bracket only has to CONTAIN the median, so the two order statistics are resolved to the
+// top 22 key bits (exponent + 11 mantissa bits, 0.05 % in magnitude) with two histogram passes
+// over the sample and then rounded outwards.
 __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, Bracket* br) {
-    __shared__ SelectScratch sc;
+    __shared__ uint32_t h1[RADIX], h2lo[RADIX], h2hi[RADIX];
+    __shared__ uint32_t s_blo, s_bhi, s_rlo, s_rhi, s_slo, s_shi;
     const int ip = blockIdx.x;
     const uint64_t* c = w.cand + (size_t)ip * w.cand_cap;
     const double delta = 3.0 / sqrt((double)S);
     long long rlo = (long long)floor((0.5 - delta) * S), rhi = (long long)ceil((0.5 + delta) * S);
     if (rlo < 0) rlo = 0;
     if (rhi > (long long)S - 1) rhi = S - 1;
-    const uint64_t klo = select_rank(c, S, (uint64_t)rlo, &sc);
-    const uint64_t khi = select_rank(c, S, (uint64_t)rhi, &sc);
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) { h1[i] = 0; h2lo[i] = 0; h2hi[i] = 0; }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) atomicAdd(&h1[(unsigned)(c[i] >> 52) & (RADIX - 1)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 2) {  // thread 0: lower rank, thread 1: upper rank
+        uint32_t r = threadIdx.x == 0 ? (uint32_t)rlo : (uint32_t)rhi;
+        int b = 0;
+        for (; b < RADIX - 1; b++) { if (r < h1[b]) break; r -= h1[b]; }
+        if (threadIdx.x == 0) { s_blo = b; s_rlo = r; } else { s_bhi = b; s_rhi = r; }
+    }
+    __syncthreads();
+    const uint32_t blo = s_blo, bhi = s_bhi;
+    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+        const uint64_t k = c[i];
+        const uint32_t top = (unsigned)(k >> 52) & (RADIX - 1), sub = (unsigned)(k >> 41) & (RADIX - 1);
+        if (top == blo) atomicAdd(&h2lo[sub], 1u);
+        if (top == bhi) atomicAdd(&h2hi[sub], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const uint32_t* h = threadIdx.x == 0 ? h2lo : h2hi;
+        uint32_t r = threadIdx.x == 0 ? s_rlo : s_rhi;
+        int b = 0;
+        for (; b < RADIX - 1; b++) { if (r < h[b]) break; r -= h[b]; }
+        if (threadIdx.x == 0) s_slo = b; else s_shi = b;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
+        const uint64_t klo = ((uint64_t)blo << 52) | ((uint64_t)s_slo << 41);                              // lower edge
+        const uint64_t khi = ((((uint64_t)bhi << 11) | (uint64_t)s_shi) + 1 << 41) - 1;                      // upper edge
         const double lo = __longlong_as_double((long long)klo), hi = __longlong_as_double((long long)khi);
         br[ip].qlo = lo * lo * (1.0 - 1e-9);
-        br[ip].qhi = hi * hi * (1.0 + 1e-9);
+        br[ip].qhi = (khi >= 0x7ff0000000000000ull) ? __longlong_as_double(0x7ff0000000000000LL) : hi * hi * (1.0 + 1e-9);
         w.cand_n[ip] = 0;  // becomes the member fill counter
     }
 }
