@@ -267,17 +267,14 @@ def run_ours(args):
         ctx.embed_batch_dev(d_cover, d_bins, d_bits, d_stego, usable=d_usable, median=d_median, **PARAMS)
         ctx.extract_frame_dev(d_stego, d_bins, 912, d_hdr, d_pay, alpha=PARAMS["alpha"], center=PARAMS["center"])
 
+    from steganosaurus_b200 import shard
+    timing = shard.Timing(dist, dev)  # the helpers tests/test_shard_gloo.py exercises with gloo
+
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        timing.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = timing.max_over_ranks
 
     # ---- device-resident leg ("value")
     for _ in range(args.warmup):
@@ -353,7 +350,7 @@ def run_ours(args):
                 traffic = tj["dram_bytes_per_image"] * (B * args.steps * (2 if name in ("row_fwd_u8", "col_fwd") else 1)) / groups
         except Exception:
             pass
-    mp_per_step = B * W * H / 1e6
+    mp_per_step = B * W * H / 1e6   # per rank; every rank runs the same batch size (weak scaling)
     line = {
         "metric": METRIC, "value": world * mp_per_step / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
