@@ -1,0 +1,130 @@
+"""Cross-tool drop-in tests (GPU): the new `turtlefft` CLI (CUDA hot path) against the reference CLI
+compiled from the unmodified sources (oracle/_ref/turtlefft).  Reference-embedded images must
+extract with the new tool and vice versa, with the same messages and exit codes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from steganosaurus_b200 import host, synth
+import steganosaurus_b200 as sb
+
+pytestmark = pytest.mark.gpu
+
+OURS = os.path.join(os.path.dirname(os.path.abspath(sb.__file__)), "turtlefft")
+REF = O.REF_CLI
+PASS = "correct horse battery staple"
+MSG = "the eagle has landed"
+
+
+def run(exe, *args, timeout=300):
+    p = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=timeout)
+    return p.returncode, p.stdout, p.stderr
+
+
+@pytest.fixture(scope="module")
+def tools():
+    if not os.path.exists(REF):
+        pytest.skip("reference CLI not shipped (oracle/_ref/turtlefft)")
+    assert os.path.exists(OURS), "steganosaurus_b200/turtlefft not built"
+    return OURS, REF
+
+
+@pytest.fixture(scope="module")
+def cover512(tmp_path_factory):
+    p = str(tmp_path_factory.mktemp("cli") / "host512.png")
+    host.png_save(p, synth.gen_cover(512, 512, 7))
+    return p
+
+
+@pytest.mark.parametrize("flags", [[], ["--center", "1"], ["--alpha", "0.18", "--density", "0.5"], ["--rmin", "0.1", "--rmax", "0.3"],
+                                   ["--jitter", "0.05"], ["--alpha", "0.22", "--jitter", "0.05"]])
+def test_c1_roundtrips_all_four_ways(tools, cover512, tmp_path, flags):
+    ours, ref = tools
+    common = ["--pass", PASS, "--pbkdf2_iter", "1000", *flags]
+    s_ours, s_ref = str(tmp_path / "ours.png"), str(tmp_path / "ref.png")
+    rc, out, err = run(ours, "embed", "--in", cover512, "--out", s_ours, "--secret", MSG, *common)
+    assert rc == 0, err
+    assert out.strip() == f"Embedded 2928 bits into {s_ours} (payload 20 bytes, ver=2, salt/nonce in header)"
+    rc, out, err = run(ref, "embed", "--in", cover512, "--out", s_ref, "--secret", MSG, *common)
+    assert rc == 0, err
+    for tool in (ours, ref):
+        for stego in (s_ours, s_ref):
+            rc, out, err = run(tool, "extract", "--in", stego, *common)
+            assert (rc, out) == (0, MSG + "\n"), (tool, stego, err)
+
+
+def test_same_salt_gives_identical_stego_pixels(tools, cover512, tmp_path):
+    """With the salt pinned the new CLI's stego image equals the oracle's embed of the same frame."""
+    ours, _ = tools
+    s = str(tmp_path / "fixed.png")
+    salt = bytes(range(16))
+    rc, _, err = run(ours, "embed", "--in", cover512, "--out", s, "--secret", MSG, "--pass", "pw", "--pbkdf2_iter", "1000",
+                     "--salt-hex", salt.hex())
+    assert rc == 0, err
+    r = O.ref()
+    bits, _ = r.frame_bits(b"pw", salt, 1000, MSG.encode())
+    bins, _, _ = r.walk(b"pw", 512, 512, bits.size)
+    want = r.embed(host.png_load(cover512), bins, bits)["stego"]
+    got = host.png_load(s)
+    d = np.abs(got.astype(int) - want.astype(int))
+    assert d.max() <= 1 and (d == 0).mean() > 0.9999
+
+
+def test_failure_messages_match_reference(tools, cover512, tmp_path):
+    ours, ref = tools
+    s = str(tmp_path / "s.png")
+    assert run(ours, "embed", "--in", cover512, "--out", s, "--secret", MSG, "--pass", PASS, "--pbkdf2_iter", "1000")[0] == 0
+    for tool in (ours, ref):
+        rc, out, err = run(tool, "extract", "--in", s, "--pass", "wrong", "--pbkdf2_iter", "1000")
+        assert (rc, out, err) == (1, "", "Magic not found.\n"), tool                                    # S:1237
+        rc, out, err = run(tool, "extract", "--in", s, "--pass", PASS, "--pbkdf2_iter", "1001")
+        assert (rc, out, err) == (1, "", "Auth failed (wrong pass or data corrupted).\n"), tool       # S:1308
+        rc, out, err = run(tool, "extract", "--in", s, "--pass", PASS, "--pbkdf2_iter", "1000", "--density", "0.5")
+        assert (rc, err) == (1, "Magic not found.\n"), tool
+        rc, out, err = run(tool, "extract", "--in", str(tmp_path / "nope.png"), "--pass", PASS)
+        assert rc == 1 and err == f"Failed to load {tmp_path / 'nope.png'}\n"
+        rc, out, err = run(tool, "embed", "--in", cover512, "--bogus", "1")
+        assert rc == 1 and err.startswith("Unknown arg: --bogus\n")
+
+
+def test_capacity_message_matches_reference(tools, tmp_path):
+    ours, ref = tools
+    c = str(tmp_path / "host256.png")
+    host.png_save(c, synth.gen_cover(256, 256, 5))
+    secret = "x" * 400
+    outs = []
+    for tool in (ours, ref):
+        rc, out, err = run(tool, "embed", "--in", c, "--out", str(tmp_path / "o.png"), "--secret", secret, "--pass", PASS,
+                           "--pbkdf2_iter", "1000")
+        assert rc == 1 and out == ""
+        outs.append(err)
+    assert outs[0] == outs[1] == "Message too large. Need 24208 bits (after ECC), capacity ~15288 bits.\n"   # S:1010
+
+
+def test_non_pow2_fails_like_reference(tools, tmp_path):
+    """on padded sizes the crop destroys the signal and the reference's own extract fails."""
+    ours, ref = tools
+    c = str(tmp_path / "c.png")
+    host.png_save(c, synth.gen_cover(640, 360, 3))
+    s = str(tmp_path / "s.png")
+    assert run(ours, "embed", "--in", c, "--out", s, "--secret", MSG, "--pass", PASS, "--pbkdf2_iter", "1000")[0] == 0
+    for tool in (ours, ref):
+        rc, out, err = run(tool, "extract", "--in", s, "--pass", PASS, "--pbkdf2_iter", "1000")
+        assert (rc, err) == (1, "Magic not found.\n"), tool
+
+
+def test_c2_pow2_8kb_payload_python_driver(ctx):
+    """C2 (pow2 variant): 2048x2048, 8192-byte payload, do_embed/do_extract mirrors on the CUDA path."""
+    rng = np.random.default_rng(1)
+    secret = bytes(rng.integers(32, 127, 8192, dtype=np.uint8))
+    cover = synth.gen_texture(2048, 2048, 1, sigma=12.0)
+    stego, nbits = host.embed_image(ctx, cover, secret, PASS.encode(), pbkdf2_iter=1000)
+    assert nbits == 460560
+    assert host.extract_image(ctx, stego, PASS.encode(), pbkdf2_iter=1000) == secret
+    with pytest.raises(host.ExtractError, match="Magic not found"):
+        host.extract_image(ctx, stego, b"wrong", pbkdf2_iter=1000)
+    with pytest.raises(host.ExtractError, match="Auth failed"):
+        host.extract_image(ctx, stego, PASS.encode(), pbkdf2_iter=999)
