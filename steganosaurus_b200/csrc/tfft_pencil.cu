@@ -23,6 +23,8 @@
 // Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
 #include "tfft_kernels.cuh"
 
+#include <cstdlib>
+
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace tfft {
@@ -992,6 +994,11 @@ template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, CO
 template <int LOG2N>
 cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     using C = Cfg<LOG2N>;
+    if constexpr (LOG2N == 12) {  // experiment switch: one unit per CTA (how much do two units overlap?)
+        static const bool one_unit = getenv("TFFT_ROW_UNITS") && atoi(getenv("TFFT_ROW_UNITS")) == 1;
+        if (one_unit && p.half && p.img_in) return run_r2c<LOG2N, 1, false>(L, p);
+        if (one_unit && p.half && p.img_out) return run_r2c<LOG2N, 1, true>(L, p);
+    }
     if (p.half && p.img_in) return run_r2c<LOG2N, C::U8F_UNITS, false>(L, p);
     if (p.half && p.img_out) return run_r2c<LOG2N, C::U8I_UNITS, true>(L, p);
     if (p.img_in) return run_u8<LOG2N, C::U8F_UNITS, false>(L, p);
