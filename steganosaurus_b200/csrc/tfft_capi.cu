@@ -23,7 +23,7 @@ struct DevBuf {
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf spec, in, out, bits, med, medians, usable, outbytes, raw;
+    DevBuf spec, spec2, in, out, bits, med, medians, usable, outbytes, raw;  // spec2: scratch of the four-step passes (dims > 4096)
     // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
     // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
     // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
@@ -101,6 +101,7 @@ struct Geom {
     size_t P;          // PH*PW
     size_t img_bytes;  // H*W*3
     int half, ld;      // workspace layout (SpecLayout)
+    int large;         // a padded dimension exceeds 4096: unfused conversion + four-step passes, full spectrum
     size_t E;          // stored elements per plane = PH*ld
     SpecLayout lay() const { return SpecLayout{PH, PW, ld, half}; }
 };
@@ -117,6 +118,7 @@ int make_geom(const tfft_ctx* ctx, int W, int H, Geom& g) {
     g.img_bytes = (size_t)W * H * 3;
     // half-spectrum workspace whenever both axes run on the pencil kernels (512..4096 points)
     g.half = (ctx && ctx->use_half && ctx->fft_impl != 0 && g.lw >= 9 && g.lw <= 12 && g.lh >= 9 && g.lh <= 12) ? 1 : 0;
+    g.large = (ctx && ctx->fft_impl != 0 && (g.lw > 12 || g.lh > 12)) ? 1 : 0;
     g.ld = g.half ? g.PW / 2 + 16 : g.PW;
     g.E = (size_t)g.PH * g.ld;
     return TFFT_OK;
@@ -164,7 +166,7 @@ void prof_drain(tfft_ctx* c) {
 
 // images per chunk so that `nslots` spectrum workspaces fit the limit
 int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
-    const size_t per_img = 3 * g.E * sizeof(double2);
+    const size_t per_img = 3 * g.E * sizeof(double2) * (g.large ? 2 : 1);
     size_t c = ctx->ws_limit / nslots / per_img;
     if (c < 1) c = 1;
     if (c > (size_t)MAX_CHUNK) c = MAX_CHUNK;
@@ -176,6 +178,7 @@ int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, 
     int rc;
     const int nplanes = chunk * 3;
     if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
+    if (g.large && (rc = ensure(ctx, S.spec2, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
     if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, CAND_CAP)))) return rc;
     if ((rc = ensure(ctx, S.medians, sizeof(double) * nplanes))) return rc;
     if ((rc = ensure(ctx, S.usable, sizeof(uint64_t) * chunk))) return rc;
@@ -215,8 +218,17 @@ PassArgs base_args(tfft_ctx* ctx, double2* spec, int nimg, const Geom& g, int ce
 }
 
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
-int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_t* d_img, int nimg, const Geom& g, int center) {
+int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
+    if (g.large) {  // unfused: u8 -> planes (zero pad materialised), then two generic c2c passes
+        { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_u8_to_planes(L, d_img, spec, nimg, g.W, g.H, g.PW, g.PH, center)); }
+        a.tmp = tmp; a.inverse = 0;
+        a.axis = 0; a.log2n = g.lw;
+        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        a.axis = 1; a.log2n = g.lh;
+        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        return TFFT_OK;
+    }
     const double cols = (double)g.ld;  // columns the workspace keeps (PW, or PW/2+16 in half mode)
     a.img_in = d_img;
     a.axis = 0; a.log2n = g.lw; a.inverse = 0;
@@ -231,8 +243,17 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, const uint8_
 
 // inverse 2-D FFT + crop + quantise (S:1100-1103): columns first so that the last pass runs
 // along image rows and can emit interleaved u8 directly.
-int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, uint8_t* d_img, int nimg, const Geom& g, int center) {
+int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
+    if (g.large) {
+        a.tmp = tmp; a.inverse = 1;
+        a.axis = 1; a.log2n = g.lh;
+        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        a.axis = 0; a.log2n = g.lw;
+        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_planes_to_u8(L, spec, d_img, nimg, g.W, g.H, g.PW, g.PH, center)); }
+        return TFFT_OK;
+    }
     const double cols = (double)g.ld;
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403): the column pass does not store them
@@ -250,7 +271,7 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
                 double alpha, int center, double magmin, double rmin, double rmax,
                 uint8_t* d_stego, uint64_t* d_usable, double* d_median) {
     double2* spec = (double2*)S.spec.p;
-    int rc = forward_images(ctx, L, spec, d_cover, nimg, g, center);
+    int rc = forward_images(ctx, L, spec, (double2*)S.spec2.p, d_cover, nimg, g, center);
     if (rc) return rc;
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
@@ -259,7 +280,7 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
       CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
     { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
       CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
-    return inverse_images(ctx, L, spec, d_stego, nimg, g, center);
+    return inverse_images(ctx, L, spec, (double2*)S.spec2.p, d_stego, nimg, g, center);
 }
 
 // nhdr == 0: one segment of `rep`; nhdr > 0: rep-3 header segment + rep-7 payload segment (S:1223-1268)
@@ -267,7 +288,7 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
                   const uint32_t* d_bins, size_t nbins, int rep, size_t nhdr, const double* d_jitter, double alpha, int center,
                   uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw) {
     double2* spec = (double2*)S.spec.p;
-    int rc = forward_images(ctx, L, spec, d_stego, nimg, g, center);
+    int rc = forward_images(ctx, L, spec, (double2*)S.spec2.p, d_stego, nimg, g, center);
     if (rc) return rc;
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
@@ -365,7 +386,7 @@ void tfft_destroy(tfft_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
-        release(S.spec); release(S.in); release(S.out); release(S.bits); release(S.med);
+        release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.med);
         release(S.medians); release(S.usable); release(S.outbytes); release(S.raw);
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
@@ -617,12 +638,12 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    if ((size_t)n * 3 * g.E * sizeof(double2) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
+    if ((size_t)n * 3 * g.E * sizeof(double2) * (g.large ? 2 : 1) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
     Slot& S = ctx->slot[0];
     if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
     Launcher L = make_launcher(ctx, S.stream);
-    if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (const uint8_t*)S.in.p, n, g, center))) return rc;
+    if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center))) return rc;
     CK(cudaStreamSynchronize(S.stream));
     ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay();
     return TFFT_OK;
@@ -672,9 +693,19 @@ int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int c
 }
 
 // ---------------------------------------------------------------------------------------------
+static int hook_scratch(tfft_ctx* ctx, int nplanes, int PH, int PW, double2** tmp) {
+    *tmp = nullptr;
+    if (ctx->fft_impl == 0 || (PH <= 4096 && PW <= 4096)) return TFFT_OK;
+    int rc = ensure(ctx, ctx->full, (size_t)nplanes * PH * PW * sizeof(double2));
+    if (rc) return rc;
+    *tmp = (double2*)ctx->full.p;
+    return TFFT_OK;
+}
+
 static int fft2d_planes(tfft_ctx* ctx, const Launcher& L, double2* d, int nplanes, int PH, int PW, int inverse) {
     PassArgs a;
     memset(&a, 0, sizeof(a));
+    { int rc = hook_scratch(ctx, nplanes, PH, PW, &a.tmp); if (rc) return rc; }
     a.spec = d; a.tw = ctx->d_tw; a.nplanes = nplanes;
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
     a.in_rows = PH; a.out_rows = PH; a.inverse = inverse; a.ld = PW;
@@ -708,6 +739,7 @@ int tfft_fft_pass_dev(tfft_ctx* ctx, double* d_data, int n, int PH, int PW, int 
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
     PassArgs a;
     memset(&a, 0, sizeof(a));
+    if ((rc = hook_scratch(ctx, n, PH, PW, &a.tmp))) return rc;
     a.spec = (double2*)d_data; a.tw = ctx->d_tw; a.nplanes = n;
     a.W = PW; a.H = PH; a.PW = PW; a.PH = PH;
     a.in_rows = PH; a.out_rows = PH; a.inverse = inverse; a.ld = PW;

@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(512) fft_pass_v0(PassArgs a, int cpc) {
     }
 }
 
+cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& a, bool* handled);
+
 static cudaError_t launch_v0(const Launcher& L, const PassArgs& a) {
     const int n = 1 << a.log2n;
     const size_t per = (size_t)n * sizeof(double2);
@@ -164,10 +166,89 @@ static cudaError_t launch_v0(const Launcher& L, const PassArgs& a) {
     return cudaSuccess;
 }
 
-cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& a, bool* handled);
+// --------------------------------------------------------------------------------------------
+// Four-step scheme for pencils longer than 4096 points (8192 = 2*4096, 16384 = 4*4096).
+//   x[R*m + r]  --M-point FFT over m for every r-->  Y_r[k]          (in place: a length-N pencil
+//                 viewed as an [M][R] matrix makes the R strided sub-sequences its columns, so the
+//                 sub-transforms are exactly a column pass of the 4096-point pencil kernel)
+//   X[k + M*q] = sum_r w_R^{rq} * w_N^{rk} * Y_r[k]                   (radix-R combine, spec -> tmp)
+// and the result is copied back so the pass stays in place for its callers.
+// --------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(256) fourstep_combine(const double2* __restrict__ src, double2* __restrict__ dst,
+                                                        const double2* __restrict__ tw, int axis, int PH, int PW,
+                                                        int log2n, int inverse, long long total) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int N = 1 << log2n, M = N / R;
+    size_t in0, in_stride, out0, out_stride;
+    int k;
+    if (axis == 0) {  // pencil = one row of PW = N points; consecutive threads -> consecutive k
+        k = (int)(t % M);
+        const size_t row = (size_t)(t / M);  // plane*PH + y
+        in0 = row * N + (size_t)R * k; in_stride = 1;
+        out0 = row * N + k; out_stride = M;
+    } else {          // pencil = one column of PH = N points; consecutive threads -> consecutive x
+        const int x = (int)(t % PW);
+        const long long u = t / PW;
+        k = (int)(u % M);
+        const size_t plane = (size_t)(u / M);
+        in0 = plane * (size_t)N * PW + (size_t)R * k * PW + x; in_stride = PW;
+        out0 = plane * (size_t)N * PW + (size_t)k * PW + x; out_stride = (size_t)M * PW;
+    }
+    double2 y[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        double2 v = src[in0 + (size_t)r * in_stride];
+        if (r) {  // w_N^{r k}: table holds exp(+2 pi i j / 16384), j < 8192; the other half by w^{j+8192} = -w^j
+            unsigned j = (unsigned)(r * k) << (TW_LOG2 - log2n);
+            double2 w = tw[j & (TW_N / 2 - 1)];
+            if (j & (TW_N / 2)) { w.x = -w.x; w.y = -w.y; }
+            if (inverse) w.y = -w.y;
+            v = make_double2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+        }
+        y[r] = v;
+    }
+    const double sc = inverse ? 1.0 / R : 1.0;  // the sub-transforms already scaled by 1/M (S:357)
+    if (R == 2) {
+        dst[out0] = make_double2((y[0].x + y[1].x) * sc, (y[0].y + y[1].y) * sc);
+        dst[out0 + out_stride] = make_double2((y[0].x - y[1].x) * sc, (y[0].y - y[1].y) * sc);
+    } else {
+        const double s = inverse ? -1.0 : 1.0;  // w_4 = s*i
+        const double2 t0 = make_double2(y[0].x + y[2].x, y[0].y + y[2].y), t1 = make_double2(y[0].x - y[2].x, y[0].y - y[2].y);
+        const double2 t2 = make_double2(y[1].x + y[3].x, y[1].y + y[3].y);
+        const double2 d = make_double2(y[1].x - y[3].x, y[1].y - y[3].y);
+        const double2 t3 = make_double2(-s * d.y, s * d.x);  // s*i*(y1 - y3)
+        dst[out0] = make_double2((t0.x + t2.x) * sc, (t0.y + t2.y) * sc);
+        dst[out0 + out_stride] = make_double2((t1.x + t3.x) * sc, (t1.y + t3.y) * sc);
+        dst[out0 + 2 * out_stride] = make_double2((t0.x - t2.x) * sc, (t0.y - t2.y) * sc);
+        dst[out0 + 3 * out_stride] = make_double2((t1.x - t3.x) * sc, (t1.y - t3.y) * sc);
+    }
+}
+
+static cudaError_t launch_fourstep(const Launcher& L, const PassArgs& a) {
+    const int R = 1 << (a.log2n - 12), M = 4096;
+    // sub-transforms: column pass of the reshaped batch
+    PassArgs s = a;
+    s.axis = 1; s.log2n = 12; s.half = 0; s.img_in = nullptr; s.img_out = nullptr;
+    if (a.axis == 0) { s.nplanes = a.nplanes * a.PH; s.PH = M; s.PW = R; }          // every row is an [M][R] matrix
+    else             { s.PH = M; s.PW = R * a.PW; }                               // plane [N][PW] seen as [M][R*PW]
+    s.ld = s.PW; s.in_rows = M; s.out_rows = M; s.W = s.PW; s.H = s.PH;
+    bool handled = false;
+    cudaError_t e = launch_fft_pass_pencil(L, s, &handled);
+    if (e != cudaSuccess) return e;
+    if (!handled) return cudaErrorNotSupported;
+    const long long total = (long long)a.nplanes * a.PH * a.PW / R;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (R == 2) fourstep_combine<2><<<grid, 256, 0, L.stream>>>(a.spec, a.tmp, a.tw, a.axis, a.PH, a.PW, a.log2n, a.inverse, total);
+    else        fourstep_combine<4><<<grid, 256, 0, L.stream>>>(a.spec, a.tmp, a.tw, a.axis, a.PH, a.PW, a.log2n, a.inverse, total);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaMemcpyAsync(a.spec, a.tmp, (size_t)a.nplanes * a.PH * a.PW * sizeof(double2), cudaMemcpyDeviceToDevice, L.stream);
+}
 
 cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a) {
     if (L.fft_impl != 0) {
+        if (a.log2n > 12 && a.log2n <= 14 && a.tmp && !a.img_in && !a.img_out && !a.half) return launch_fourstep(L, a);
         bool handled = false;
         cudaError_t e = launch_fft_pass_pencil(L, a, &handled);
         if (e != cudaSuccess || handled) return e;
@@ -741,6 +822,50 @@ cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, Spe
     return cudaSuccess;
 }
 
+
+// ---- unfused conversions for the large-size path (to_planes_u8 S:383 + apply_center S:392 + pad_to_fft S:393;
+//      ifft_crop S:399 + apply_center S:1102 + from_planes_u8 S:387)
+__global__ void __launch_bounds__(256) u8_to_planes(const uint8_t* __restrict__ img, double2* __restrict__ spec, int W, int H, int PW, int PH,
+                                                    int center, long long total) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int x = (int)(t % PW);
+    const long long u = t / PW;
+    const int y = (int)(u % PH);
+    const long long ip = u / PH;  // image*3 + plane
+    double v = 0.0;
+    if (x < W && y < H) {
+        v = (double)img[(((size_t)(ip / 3) * H + y) * W + x) * 3 + (ip % 3)];
+        if (center && ((x + y) & 1)) v = -v;
+    }
+    spec[t] = make_double2(v, 0.0);
+}
+__global__ void __launch_bounds__(256) planes_to_u8(const double2* __restrict__ spec, uint8_t* __restrict__ img, int W, int H, int PW, int PH,
+                                                    int center, long long total) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per output byte
+    if (t >= total) return;
+    const int ch = (int)(t % 3);
+    const long long px = t / 3;
+    const int x = (int)(px % W);
+    const long long u = px / W;
+    const int y = (int)(u % H);
+    const long long im = u / H;
+    double v = spec[(((size_t)im * 3 + ch) * PH + y) * PW + x].x;
+    if (center && ((x + y) & 1)) v = -v;
+    img[t] = clamp8(v);
+}
+cudaError_t launch_u8_to_planes(const Launcher& L, const uint8_t* img, double2* spec, int nimg, int W, int H, int PW, int PH, int center) {
+    const long long total = (long long)nimg * 3 * PH * PW;
+    u8_to_planes<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(img, spec, W, H, PW, PH, center, total);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+cudaError_t launch_planes_to_u8(const Launcher& L, const double2* spec, uint8_t* img, int nimg, int W, int H, int PW, int PH, int center) {
+    const long long total = (long long)nimg * H * W * 3;
+    planes_to_u8<<<(unsigned)((total + 255) / 256), 256, 0, L.stream>>>(spec, img, W, H, PW, PH, center, total);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
 
 // full[y][x] from a half-spectrum workspace (parity hook only)
 __global__ void expand_half(const double2* __restrict__ hs, double2* __restrict__ fs, SpecLayout lay) {

@@ -37,6 +37,9 @@ struct PassArgs {
     // plane of PW := ld columns.
     int half;
     int ld;
+    // Scratch plane batch of the same size as spec: needed by passes longer than 4096 points
+    // (four-step scheme: strided 4096-point sub-transforms in place, radix-2/4 combine through tmp).
+    double2* tmp;
 };
 
 // How a plane's spectrum is stored.  full: [PH][PW], ld = PW.  half (real planes, Hermitian):
@@ -85,6 +88,10 @@ cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout 
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout lay,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
                            uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+
+// unfused image <-> plane conversion for sizes the fused row passes do not cover (PW or PH > 4096)
+cudaError_t launch_u8_to_planes(const Launcher& L, const uint8_t* img, double2* spec, int nimg, int W, int H, int PW, int PH, int center);
+cudaError_t launch_planes_to_u8(const Launcher& L, const double2* spec, uint8_t* img, int nimg, int W, int H, int PW, int PH, int center);
 
 // full[y][x] from the half layout (parity hook tfft_forward_spectrum)
 cudaError_t launch_expand_half(const Launcher& L, const double2* half_spec, double2* full_spec, int nplanes, SpecLayout lay);

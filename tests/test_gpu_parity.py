@@ -30,7 +30,7 @@ def assert_pixels(a, b):
 
 @pytest.mark.parametrize("PH,PW,n", [(16, 16, 3), (32, 64, 2), (64, 16, 1), (128, 128, 4), (512, 512, 5), (256, 1024, 1),
                                      (2048, 512, 3), (4096, 64, 1), (64, 8192, 1), (1024, 2048, 2), (512, 4096, 1),
-                                     (4096, 1024, 1), (2048, 2048, 1)])
+                                     (4096, 1024, 1), (2048, 2048, 1), (8192, 512, 1), (64, 16384, 2), (16384, 32, 1), (8192, 8192, 1)])
 def test_fft2d_matches_oracle(ctx, PH, PW, n):
     rng = np.random.default_rng(PH * 31 + PW)
     a = rng.standard_normal((n, PH, PW)) + 1j * rng.standard_normal((n, PH, PW))
@@ -39,7 +39,8 @@ def test_fft2d_matches_oracle(ctx, PH, PW, n):
         got = ctx.fft2d(a, inverse=inv)
         want = np.stack([o.fft2d(a[i], inv) for i in range(n)])
         e = spec_err(got, want)
-        assert e[0] < SPEC_TOL and e[1] < 1e-13, (PH, PW, inv, e)
+        # the oracle itself carries ~len*eps error from its twiddle recurrence (S:353): looser L2 bar for long pencils
+        assert e[0] < SPEC_TOL and e[1] < (1e-13 if max(PH, PW) <= 4096 else 2e-12), (PH, PW, inv, e)
     # round trip is the identity
     back = ctx.fft2d(ctx.fft2d(a), inverse=True)
     assert np.abs(back - a).max() < 1e-12
@@ -91,7 +92,8 @@ def test_golden_embed_extract(ctx, name):
 @pytest.mark.parametrize("W,H,nbits,center,alpha", [
     (256, 256, 2480, False, 0.5), (512, 512, 60000, False, 0.5), (500, 300, 5000, True, 0.3),
     (1024, 512, 30000, False, 0.18), (640, 480, 8000, False, 0.5), (1100, 600, 20000, True, 0.5),
-    (2048, 1024, 50000, False, 0.5), (513, 1025, 9000, False, 0.5), (3000, 200, 4000, False, 0.5)])
+    (2048, 1024, 50000, False, 0.5), (513, 1025, 9000, False, 0.5), (3000, 200, 4000, False, 0.5),
+    (5000, 300, 6000, False, 0.5), (700, 9000, 6000, True, 0.5)])
 def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
     o = oracle()
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
