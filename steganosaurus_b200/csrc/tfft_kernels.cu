@@ -538,14 +538,19 @@ __global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ s
     const uint64_t per_cta = (P + gridDim.x - 1) / gridDim.x;
     const uint64_t lo = (uint64_t)blockIdx.x * per_cta, hi = lo + per_cta < P ? lo + per_cta : P;
     (void)step;
+    // column of this thread's first element; advanced incrementally (no 64-bit division per element)
+    const uint32_t ld = (uint32_t)lay.ld, adv = blockDim.x % ld;
+    uint32_t xcol = (uint32_t)((lo + threadIdx.x) % (uint64_t)ld);
     for (uint64_t base = lo; base < hi; base += (uint64_t)blockDim.x * SCAN_UNROLL) {
         double2 z[SCAN_UNROLL];
         int wt[SCAN_UNROLL];
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
             const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
-            wt[u] = i < hi ? col_weight(lay, (int)(i % (uint64_t)lay.ld)) : 0;
+            wt[u] = i < hi ? col_weight(lay, (int)xcol) : 0;
             z[u] = i < hi ? pl[i] : make_double2(0.0, 0.0);
+            xcol += adv;
+            if (xcol >= ld) xcol -= ld;
         }
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
@@ -614,8 +619,9 @@ __global__ void __launch_bounds__(256) capacity_count(const double2* __restrict_
     const double2* pl = spec + (size_t)ip * lay.plane_elems();
     const long long box = (long long)(ymax + 1) * (xmax + 1);
     unsigned local = 0;
+    const unsigned bw = (unsigned)(xmax + 1);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < box; i += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)(i / (xmax + 1)), x = (int)(i % (xmax + 1));
+        const int y = (int)((unsigned)i / bw), x = (int)((unsigned)i % bw);  // box < 2^32
         if (y == 0 || x == 0 || y == PH / 2 || x == PW / 2) continue;  // PH, PW are even powers of two
         const double r = sqrt((double)((long long)y * y + (long long)x * x));  // == hypot for exact integer sums
         if (r < rlo || r > rhi) continue;
