@@ -66,7 +66,7 @@ namespace {
 
 constexpr uint32_t CAND_CAP = 1u << 19;  // median: sample (<= 2^18 keys) and bracket members per plane
 constexpr int MAX_CHUNK = 64;
-constexpr int HOST_CHUNK = 16;  // host-buffer entry points: small chunks so H2D / kernels / D2H of neighbouring chunks overlap
+static int HOST_CHUNK = 8;  // host-buffer entry points: small chunks so H2D / kernels / D2H of neighbouring chunks overlap (TFFT_HOST_CHUNK)
 
 int fail_cuda(tfft_ctx* c, cudaError_t e, const char* where) {
     snprintf(c->cuda_err, sizeof(c->cuda_err), "%.160s: %.80s", where, cudaGetErrorString(e));
@@ -369,6 +369,7 @@ int tfft_create(int device, tfft_ctx** out) {
     ctx->ws_limit = (size_t)((double)tot * 0.40);
     const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
     ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
+    if (const char* hc = getenv("TFFT_HOST_CHUNK")) { int v = atoi(hc); if (v >= 1 && v <= MAX_CHUNK) HOST_CHUNK = v; }
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
     for (int i = 0; i < NSLOT; i++)

@@ -24,6 +24,7 @@
 #include "tfft_kernels.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
@@ -451,6 +452,109 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma(const __grid_constant__
 #pragma unroll 1
                 for (int j = 0; j < NBOX / 2; j++)
                     tma_store_3d(&out_map, STG + (size_t)j * BOX_ROWS * VEC, g * VEC * 2, h * (G::N / 2) + j * BOX_ROWS, plane);
+                tma_commit();
+                if (h == 0) tma_wait_read_all();
+            }
+        }
+    }
+    if (tid == 0) tma_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
+// Column pass, N = 4096, two columns per CTA, warp-local second exchange.
+// After stage 1 the transform splits into sixteen independent 256-point problems (one per k1), and
+// with two lane-interleaved columns the 16 threads x 2 columns of one k1 are exactly one warp.  So
+// exchange 2 needs no block barrier: every warp transposes inside its private 4 KB slice of X
+// (re then im, XOR-swizzled) with __syncwarp, keeps (k1, k2) for stage 3 and stages its results in the
+// same slice as [k3][k2][column].  The row order that leaves behind (row = k1 + 16 k2 + 256 k3) is undone
+// by the store itself: a rank-5 tensor map (column pair, k2, k3, k1, plane) lets ONE TMA box store per
+// half pencil scatter the [k1][k3][k2] staging image to its rows.  Block barriers per pair: 5 (was 9).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];\n"
+                 ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+template <int S>
+__global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant__ CUtensorMap in_map,
+                                                           const __grid_constant__ CUtensorMap out_map, ColTmaArgs a) {
+    constexpr int LOG2N = 12, VEC = 2;
+    using G = Geo<LOG2N, VEC>;
+    constexpr int BOX_ROWS = 256, NBOX = G::N / BOX_ROWS;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar;
+    double2* L = (double2*)smem_raw;
+    double* X = (double*)(smem_raw + G::L_BYTES);
+    const int tid = threadIdx.x, c = tid & 1, tt = tid >> 1;
+    const int k1 = tt >> 4, m = tt & 15;            // warp index == k1; m doubles as k2 in stage 3
+    double* Xw = X + (size_t)k1 * 256 * VEC;        // this warp's private 4 KB slice (8 B entries)
+    double2* Sw = (double2*)Xw;                     // the same slice as staging: [k3 (8)][k2 (16)][c] 16 B entries
+    const double scale = S < 0 ? 1.0 / (double)G::N : 1.0;  // S:357
+    ThreadTw<S, LOG2N, VEC> ttw;
+    ttw.load(a.tw, tt);
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue_load = [&](long long it) {
+        const int plane = (int)(it / a.groups_per_plane), g = (int)(it % a.groups_per_plane);
+        mbar_expect_tx(&full_bar, (unsigned)G::L_BYTES);
+#pragma unroll 1
+        for (int j = 0; j < NBOX; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
+    };
+
+    const long long stride = gridDim.x;
+    long long item = blockIdx.x;
+    if (tid == 0 && item < a.nitems) issue_load(item);
+    unsigned parity = 0;
+    for (; item < a.nitems; item += stride) {
+        mbar_wait(&full_bar, parity);
+        parity ^= 1;
+        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
+        __syncthreads();
+        double2 x[16];
+        stage2_load<LOG2N, VEC>(L, tt, c, x);
+        if (tid == 0) tma_wait_read_all();  // the previous pair's last box store has finished reading X
+        __syncthreads();                    // L is free, X is free
+        if (tid == 0 && item + stride < a.nitems) {
+            fence_async_proxy();
+            issue_load(item + stride);
+        }
+        // ---- stage 2, warp-local transpose (write [k2][m ^ k2], read [k2 = m][n ^ m]), stage 3
+        dft<S, 16>(x);
+        twiddle<16>(x, ttw.s2v());
+        double2 z[16];
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].x;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) z[n].x = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        __syncwarp();
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].y;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        dft<S, 16>(z);  // z[oidx(k3)] = output row k1 + 16*m + 256*k3 of column c
+        const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (h == 1) __syncthreads();  // the first half has been read out by the TMA engine
+            __syncwarp();                 // every lane is past its reads of the slice
+#pragma unroll
+            for (int k3 = 8 * h; k3 < 8 * h + 8; k3++) {
+                double2 v = z[oidx<16>(k3)];
+                v.x *= scale; v.y *= scale;
+                Sw[((k3 - 8 * h) * 16 + m) * VEC + c] = v;
+            }
+            fence_async_proxy();
+            __syncthreads();
+            if (tid == 0) {
+                // smem image [k1][k3][k2][2 columns] -> rows k1 + 16 k2 + 256 k3 (map dims: col, k2, k3, k1, plane)
+                tma_store_5d(&out_map, X, g * VEC * 2, 0, 8 * h, 0, plane);
                 tma_commit();
                 if (h == 0) tma_wait_read_all();
             }
@@ -920,6 +1024,41 @@ bool make_col_map(CUtensorMap* m, const double2* spec, int nplanes, int PH, int 
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// store map of pencil_col_tma_w (N = 4096, VEC = 2): dims (fastest first) column doubles, k2, k3, k1, plane with
+// row = k1 + 16 k2 + 256 k3; the k3 extent clips the rows that are not needed (multiples of 256 rows)
+bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int PH, int PW, int out_rows) {
+    EncodeTiledFn enc = get_encoder();
+    if (!enc) return false;
+    const cuuint64_t rowb = (cuuint64_t)PW * 16;
+    int k3n = (out_rows + 255) / 256;
+    if (k3n > 16) k3n = 16;
+    if (k3n < 1) k3n = 1;
+    cuuint64_t dims[5] = {(cuuint64_t)2 * PW, 16, (cuuint64_t)k3n, 16, (cuuint64_t)nplanes};
+    cuuint64_t strides[4] = {16 * rowb, 256 * rowb, rowb, (cuuint64_t)PH * rowb};
+    cuuint32_t box[5] = {4, 16, 8, 16, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)spec, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int S>
+cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
+    using G = pk::Geo<12, 2>;
+    CUtensorMap in_map, out_map;
+    *ok = make_col_map(&in_map, p.spec, p.nplanes, p.PH, p.PW, p.in_rows, 2) &&
+          make_col_store_map5(&out_map, p.spec, p.nplanes, p.PH, p.PW, p.out_rows);
+    if (!*ok) return cudaSuccess;
+    pk::ColTmaArgs a;
+    a.tw = p.tw; a.groups_per_plane = p.PW / 2; a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    const size_t smem = G::L_BYTES + G::X_BYTES;
+    auto kern = pk::pencil_col_tma_w<S>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, a);
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
 template <int S, int LOG2N, int VEC>
 cudaError_t run_col_tma(const Launcher& L, const PassArgs& p, bool* ok) {
     using G = pk::Geo<LOG2N, VEC>;
@@ -1006,6 +1145,14 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     if (p.axis == 0)
         return p.inverse ? run_c2c<-1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p)
                          : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
+    if constexpr (LOG2N == 12) {  // warp-local exchange + permuting store (TFFT_COL_KERNEL=block keeps the 9-barrier kernel)
+        static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
+        if (L.fft_impl != 2 && !blockk && p.PW >= 2) {
+            bool ok = false;
+            cudaError_t e = p.inverse ? run_col_tma_w<-1>(L, p, &ok) : run_col_tma_w<+1>(L, p, &ok);
+            if (e != cudaSuccess || ok) return e;
+        }
+    }
     if (L.fft_impl != 2 && p.PW >= C::TMA_VEC) {  // TFFT_FFT_IMPL=lsu keeps the cp.async/STG column kernel
         bool ok = false;
         cudaError_t e = p.inverse ? run_col_tma<-1, LOG2N, C::TMA_VEC>(L, p, &ok) : run_col_tma<+1, LOG2N, C::TMA_VEC>(L, p, &ok);
