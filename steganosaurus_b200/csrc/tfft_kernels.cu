@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(256) capacity_count(const double2* __restrict_
     const int ip = blockIdx.y;
     const int PH = lay.PH, PW = lay.PW;
     const double thr = magmin * median[ip];
+    const double thr2_lo = thr * thr * (1.0 - 1e-12), thr2_hi = thr * thr * (1.0 + 1e-12);
     const double2* pl = spec + (size_t)ip * lay.plane_elems();
     const long long box = (long long)(ymax + 1) * (xmax + 1);
     unsigned local = 0;
@@ -626,7 +627,10 @@ __global__ void __launch_bounds__(256) capacity_count(const double2* __restrict_
         const double r = sqrt((double)((long long)y * y + (long long)x * x));  // == hypot for exact integer sums
         if (r < rlo || r > rhi) continue;
         const double2 z = spec_load(pl, lay, y, x);
-        if (hypot(z.x, z.y) < thr) continue;
+        // |F| >= thr decided on q = re^2+im^2 (2 FP64 ops); hypot() only inside a 1e-12 guard band around thr^2
+        const double q = fma(z.x, z.x, z.y * z.y);
+        if (q < thr2_lo) continue;
+        if (q <= thr2_hi && hypot(z.x, z.y) < thr) continue;
         local++;  // conjugate (PH-y, PW-x) != (y,x) is implied by the axis test
     }
     // warp + block reduce
