@@ -317,7 +317,9 @@ def run_ours(args):
         return ctx.extract_frame(hs, bins_np, 912, alpha=PARAMS["alpha"], center=PARAMS["center"])
 
     e2e_steps = max(1, args.steps)
-    for _ in range(min(args.warmup, 2)):
+    if args.no_e2e:
+        e2e_steps = 0
+    for _ in range(min(args.warmup, 2) if e2e_steps else 0):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -325,7 +327,7 @@ def run_ours(args):
         hdr, pay, _ = step_e2e()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
-    e2e_ms = max_over_ranks((t1 - t0) * 1e3) / e2e_steps
+    e2e_ms = max_over_ranks((t1 - t0) * 1e3) / max(1, e2e_steps)
     img_bytes = W * H * 3
     h2d = B * (img_bytes + nbits) + B * img_bytes + 2 * 4 * nbits
     d2h = B * img_bytes + B * 8 + B * (38 + npay)
@@ -365,7 +367,7 @@ def run_ours(args):
                    "stego_pixels_changed": round(changed, 4), "bins": "keyed turtlewalk (host), density 0.7"},
         "clocks": clocks,
         "e2e": {"value": world * mp_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
@@ -388,6 +390,7 @@ def main():
     ap.add_argument("--height", type=int, default=H_UHD)
     ap.add_argument("--payload", type=int, default=PAYLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg (the line then has no e2e)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("bench.py: note -- warmup < 3 breaks the timing rules; use only for profiling runs", file=sys.stderr)

@@ -4,6 +4,7 @@
 #include "tfft_kernels.cuh"
 
 #include <math.h>
+#include <mutex>
 #include <vector>
 
 namespace tfft {
@@ -291,9 +292,12 @@ __device__ __forceinline__ double2 spec_load(const double2* __restrict__ pl, con
 size_t median_work_bytes(int nplanes, uint32_t cand_cap) {
     size_t b = 0;
     b += (size_t)nplanes * RADIX * sizeof(uint32_t);
-    b += (size_t)nplanes * sizeof(uint64_t) * 5;  // prefix, rank, counts, bracket (2)
+    b += (size_t)nplanes * sizeof(uint64_t) * 6;  // prefix, rank, counts, bracket (2), cap_below
     b += (size_t)nplanes * cand_cap * sizeof(uint64_t);
-    b += (size_t)(nplanes + 4) * sizeof(uint32_t);  // cand_n + fallback flag
+    b += (size_t)nplanes * CAP_UNC_MAX * sizeof(uint64_t);
+    b += (size_t)nplanes * CAND_B_MAX * sizeof(uint64_t);
+    b += sizeof(uint64_t);                          // ann_total
+    b += (size_t)(3 * nplanes + 4) * sizeof(uint32_t);  // cand_n, cap_unc_n, cand_b_n, flags
     return (b + 255) & ~(size_t)255;
 }
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap) {
@@ -302,16 +306,24 @@ void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap
     w.rank = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
     w.counts = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
     w.prefix2 = (uint64_t*)p; p += (size_t)nplanes * 2 * sizeof(uint64_t);
+    w.cap_below = (uint64_t*)p; p += (size_t)nplanes * sizeof(uint64_t);
+    w.ann_total = (uint64_t*)p; p += sizeof(uint64_t);
     w.cand = (uint64_t*)p; p += (size_t)nplanes * cand_cap * sizeof(uint64_t);
+    w.cap_unc = (uint64_t*)p; p += (size_t)nplanes * CAP_UNC_MAX * sizeof(uint64_t);
+    w.cand_b = (uint64_t*)p; p += (size_t)nplanes * CAND_B_MAX * sizeof(uint64_t);
     w.hist = (uint32_t*)p; p += (size_t)nplanes * RADIX * sizeof(uint32_t);
-    w.cand_n = (uint32_t*)p;
+    w.cand_n = (uint32_t*)p; p += (size_t)nplanes * sizeof(uint32_t);
+    w.cap_unc_n = (uint32_t*)p; p += (size_t)nplanes * sizeof(uint32_t);
+    w.cand_b_n = (uint32_t*)p; p += (size_t)nplanes * sizeof(uint32_t);
+    w.flags = (int*)p;
     w.cand_cap = cand_cap;
 }
 
 __global__ void median_init(MedianWork w, int nplanes, uint64_t P) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nplanes * RADIX) w.hist[i] = 0;
-    if (i < nplanes) { w.prefix[i] = 0; w.rank[i] = P / 2; w.cand_n[i] = 0; w.counts[i] = 0; }
+    if (i < nplanes) { w.prefix[i] = 0; w.rank[i] = P / 2; w.cand_n[i] = 0; w.counts[i] = 0; w.cap_below[i] = 0; w.cap_unc_n[i] = 0; w.cand_b_n[i] = 0; }
+    if (i < 2) w.flags[i] = 0;
 }
 
 // histogram of digit d over keys whose higher digits equal prefix; grid = (chunks, nplanes)
@@ -389,7 +401,10 @@ struct SelectScratch {
     uint64_t prefix, rank;
     int top;
 };
-__device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint64_t rank, SelectScratch* sc) {
+// The multiset is { every key of c[0..n) with multiplicity wa } minus { every key of cb[0..nb) once } (cb is a
+// sub-multiset: keys whose true multiplicity is below wa).  rank is 0-based in that multiset.
+__device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint32_t wa, const uint64_t* __restrict__ cb, uint32_t nb,
+                                uint64_t rank, SelectScratch* sc) {
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     // min / max
     uint64_t mn = ~0ull, mx = 0;
@@ -417,7 +432,12 @@ __device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint
         __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
             const uint64_t k = c[i];
-            if (top == 64 || (k >> top) == (prefix >> top)) atomicAdd(&sc->hist[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
+            if (top == 64 || (k >> top) == (prefix >> top)) atomicAdd(&sc->hist[(unsigned)(k >> sft) & ((1u << wid) - 1)], wa);
+        }
+        __syncthreads();  // every +wa lands before the -1 of the same key: bins never go negative
+        for (uint32_t i = tid; i < nb; i += blockDim.x) {
+            const uint64_t k = cb[i];
+            if (top == 64 || (k >> top) == (prefix >> top)) atomicSub(&sc->hist[(unsigned)(k >> sft) & ((1u << wid) - 1)], 1u);
         }
         __syncthreads();
         // parallel bucket search: thread t owns bins 2t, 2t+1
@@ -519,91 +539,155 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
     }
 }
 
-constexpr int SCAN_UNROLL = 4;
+constexpr int SCAN_UNROLL = 8;
+constexpr int SCAN_THREADS = 512;
+constexpr uint32_t SCAN_TILE = SCAN_THREADS * SCAN_UNROLL;
 constexpr uint32_t SCAN_SBUF = 3072;  // members staged per CTA before one global reservation (24 KB)
-__global__ void __launch_bounds__(512) median_scan(const double2* __restrict__ spec, SpecLayout lay, MedianWork w, const Bracket* __restrict__ br) {
+
+// Fused capacity (count_plane S:999-1007): an annulus bin fails |F| >= magmin*median only when its q is
+// ~magmin^2 times the median's, i.e. almost never.  The scan counts the bins that certainly fail
+// (q < qcap_lo) and stages the keys of the undecided ones (qcap_lo <= q <= qcap_hi, the image of the median
+// bracket); capacity_resolve settles those against the exact median.  Off (on = 0) when the annulus
+// reaches columns the workspace does not store or every element is a member.
+struct ScanCap {
+    int on;
+    double magmin2;   // magmin^2
+    double rlo, rhi;  // annulus radii in bins
+};
+
+// A warp with at least one bracket member: ballot-compact the keys into the CTA's staging buffer.  Every stored
+// element is staged ONCE here; multiplicities are settled by the weighted select (see median_scan).
+__device__ __forceinline__ void scan_stage(bool member, double2 z, MedianWork& w, int ip, uint64_t* s_buf, unsigned* s_cnt) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, member);
+    unsigned b0 = 0;
+    if (lane == 0) b0 = atomicAdd(s_cnt, (unsigned)__popc(m));
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    if (member) {
+        const unsigned slot = b0 + __popc(m & ((1u << lane) - 1));
+        const uint64_t key = mag_key(z);
+        if (slot < SCAN_SBUF) s_buf[slot] = key;
+        else {  // staging full (pathological density): reserve directly
+            const unsigned g = atomicAdd(&w.cand_n[ip], 1u);
+            if (g < w.cand_cap) w.cand[(size_t)ip * w.cand_cap + g] = key;
+        }
+    }
+}
+
+// Truly rare (~1e-4 of the bins at magmin = 0.01): a capacity-relevant magnitude.
+__device__ __noinline__ void scan_cap_rare(double2 z, double q, uint64_t i, const SpecLayout& lay, const ScanCap& cap, double qcap_lo,
+                                           MedianWork& w, int ip, unsigned& capb) {
+    const int y = (int)(i / (uint64_t)lay.ld);
+    const int x = (int)(i - (uint64_t)y * lay.ld);
+    if (!col_weight(lay, x)) return;  // pad column
+    const bool axis = y == 0 || x == 0 || y == (lay.PH >> 1) || x == (lay.PW >> 1);  // on_axis S:698 (even sizes)
+    const double r = sqrt((double)((long long)y * y + (long long)x * x));        // == hypot for exact integer sums
+    if (axis || r < cap.rlo || r > cap.rhi) return;
+    if (q < qcap_lo) capb++;
+    else {
+        const unsigned g = atomicAdd(&w.cap_unc_n[ip], 1u);
+        if (g < CAP_UNC_MAX) w.cap_unc[(size_t)ip * CAP_UNC_MAX + g] = mag_key(z);
+    }
+}
+
+// One streaming read of the plane: weighted count of the elements below the bracket, members staged, and
+// (cap.on) the capacity verdicts.  Every stored element is counted / staged with the layout's interior
+// weight (2 for a half plane: a bin and its Hermitian mirror) in the flat main loop; the edge columns
+// (weight 1) and the zero pad columns (weight 0) are corrected per row afterwards -- counts directly, members
+// through the excess list cand_b that the weighted select subtracts -- so the hot loop carries no column
+// arithmetic.
+__global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __restrict__ spec, SpecLayout lay, MedianWork w,
+                                                            const Bracket* __restrict__ br, ScanCap cap) {
     __shared__ uint64_t s_buf[SCAN_SBUF];
-    __shared__ unsigned s_cnt, s_base, ws[16];
+    __shared__ unsigned s_cnt, s_base;
+    __shared__ long long ws[SCAN_THREADS / 32];
+    __shared__ unsigned wc[SCAN_THREADS / 32];
     const int ip = blockIdx.y;
-    const uint64_t P = lay.plane_elems();  // stored elements (weights restore the full multiset)
-    const double2* pl = spec + (size_t)ip * P;
+    const uint64_t E = lay.plane_elems();
+    const double2* pl = spec + (size_t)ip * E;
     const double qlo = br[ip].qlo, qhi = br[ip].qhi;
-    uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
+    const double qcap_lo = cap.on ? cap.magmin2 * qlo * (1.0 - 1e-9) : 0.0;
+    const double qcap_hi = cap.on ? cap.magmin2 * qhi * (1.0 + 1e-9) : -1.0;  // -1: no q qualifies
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    unsigned below = 0;
+    unsigned below = 0, capb = 0;
     const int lane = threadIdx.x & 31;
-    const uint64_t step = (uint64_t)gridDim.x * blockDim.x;
-    // each CTA owns a contiguous span so that the SCAN_UNROLL loads of a thread are independent
-    const uint64_t per_cta = (P + gridDim.x - 1) / gridDim.x;
-    const uint64_t lo = (uint64_t)blockIdx.x * per_cta, hi = lo + per_cta < P ? lo + per_cta : P;
-    (void)step;
-    // column of this thread's first element; advanced incrementally (no 64-bit division per element)
-    const uint32_t ld = (uint32_t)lay.ld, adv = blockDim.x % ld;
-    uint32_t xcol = (uint32_t)((lo + threadIdx.x) % (uint64_t)ld);
-    for (uint64_t base = lo; base < hi; base += (uint64_t)blockDim.x * SCAN_UNROLL) {
+    const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t base = t * SCAN_TILE + threadIdx.x;
         double2 z[SCAN_UNROLL];
-        int wt[SCAN_UNROLL];
+        if (base - threadIdx.x + SCAN_TILE <= E) {
 #pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; u++) {
-            const uint64_t i = base + (uint64_t)u * blockDim.x + threadIdx.x;
-            wt[u] = i < hi ? col_weight(lay, (int)xcol) : 0;
-            z[u] = i < hi ? pl[i] : make_double2(0.0, 0.0);
-            xcol += adv;
-            if (xcol >= ld) xcol -= ld;
+            for (int u = 0; u < SCAN_UNROLL; u++) z[u] = __ldcs(pl + base + (uint64_t)u * SCAN_THREADS);
+        } else {
+#pragma unroll
+            for (int u = 0; u < SCAN_UNROLL; u++) {
+                const uint64_t i = base + (uint64_t)u * SCAN_THREADS;
+                z[u] = i < E ? __ldcs(pl + i) : make_double2(qnan, 0.0);  // NaN: neither below, member nor tiny
+            }
         }
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
             const double q = fma(z[u].x, z[u].x, z[u].y * z[u].y);
-            const bool member = wt[u] && q >= qlo && q <= qhi;
-            if (q < qlo) below += wt[u];
-            // a weight-2 member (a bin and its Hermitian mirror) enters the list twice
-            for (int rep = 0; rep < 2; rep++) {
-                const bool put = member && wt[u] > rep;
-                const unsigned m = __ballot_sync(0xffffffffu, put);
-                if (!m) break;
-                unsigned b0 = 0;
-                if (lane == 0) b0 = atomicAdd(&s_cnt, (unsigned)__popc(m));
-                b0 = __shfl_sync(0xffffffffu, b0, 0);
-                if (put) {
-                    const unsigned slot = b0 + __popc(m & ((1u << lane) - 1));
-                    const uint64_t key = mag_key(z[u]);
-                    if (slot < SCAN_SBUF) s_buf[slot] = key;
-                    else {  // staging full (pathological density): reserve directly
-                        const unsigned g = atomicAdd(&w.cand_n[ip], 1u);
-                        if (g < w.cand_cap) cand[g] = key;
-                    }
+            const bool lowq = q < qlo;
+            const bool member = !lowq && q <= qhi;
+            const bool tiny = q <= qcap_hi;
+            below += lowq ? 1u : 0u;
+            if (__any_sync(0xffffffffu, member)) scan_stage(member, z[u], w, ip, s_buf, &s_cnt);
+            if (tiny) scan_cap_rare(z[u], q, base + (uint64_t)u * SCAN_THREADS, lay, cap, qcap_lo, w, ip, capb);
+        }
+    }
+    long long acc = (long long)below * (lay.half ? 2 : 1);
+    if (lay.half) {  // edge columns 0 and PW/2 carry weight 1, pad columns weight 0
+        const int h = lay.PW >> 1, nfix = lay.ld - h + 1;  // x = 0, h, h+1 .. ld-1
+        if ((int)threadIdx.x < nfix) {
+            const int x = threadIdx.x == 0 ? 0 : h + (int)threadIdx.x - 1;
+            const int over = (x == 0 || x == h) ? 1 : 2;
+            for (int y = blockIdx.x; y < lay.PH; y += gridDim.x) {
+                const double2 v = pl[(size_t)y * lay.ld + x];
+                const double q = fma(v.x, v.x, v.y * v.y);
+                if (q < qlo) acc -= over;
+                else if (q <= qhi) {  // a member staged with the interior weight: list the excess
+                    const unsigned g = atomicAdd(&w.cand_b_n[ip], (unsigned)over);
+                    const uint64_t key = mag_key(v);
+                    for (int r = 0; r < over; r++)
+                        if (g + r < CAND_B_MAX) w.cand_b[(size_t)ip * CAND_B_MAX + g + r] = key;
                 }
             }
         }
     }
-    for (int o = 16; o; o >>= 1) below += __shfl_down_sync(0xffffffffu, below, o);
-    if (lane == 0) ws[threadIdx.x >> 5] = below;
+    for (int o = 16; o; o >>= 1) { acc += __shfl_down_sync(0xffffffffu, acc, o); capb += __shfl_down_sync(0xffffffffu, capb, o); }
+    if (lane == 0) { ws[threadIdx.x >> 5] = acc; wc[threadIdx.x >> 5] = capb; }
     __syncthreads();
     const unsigned nloc = s_cnt < SCAN_SBUF ? s_cnt : SCAN_SBUF;
     if (threadIdx.x == 0) {
-        unsigned long long t = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += ws[k];
-        if (t) atomicAdd((unsigned long long*)&w.counts[ip], t);
+        long long t = 0;
+        unsigned c = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; k++) { t += ws[k]; c += wc[k]; }
+        if (t) atomicAdd((unsigned long long*)&w.counts[ip], (unsigned long long)t);  // wraps correctly for negative partial sums
+        if (c) atomicAdd((unsigned long long*)&w.cap_below[ip], (unsigned long long)c);
         s_base = nloc ? atomicAdd(&w.cand_n[ip], nloc) : 0;
     }
     __syncthreads();
+    uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
     for (unsigned i = threadIdx.x; i < nloc; i += blockDim.x)
         if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
 }
 
 // one CTA per plane: exact rank among the members, or raise the fallback flag
-__global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, double* median, int* flag, uint32_t guard) {
+__global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, uint32_t wa, double* median, int* flag, uint32_t guard) {
     __shared__ SelectScratch sc;
     const int ip = blockIdx.x;
-    const uint32_t n = w.cand_n[ip];
+    const uint32_t n = w.cand_n[ip], nb = w.cand_b_n[ip];
     const uint64_t below = w.counts[ip], rank = P / 2;
-    const bool ok = n <= w.cand_cap && rank >= below + guard && rank + guard < below + n;
+    const uint64_t total = (uint64_t)n * wa - nb;  // weighted member count
+    const bool ok = n <= w.cand_cap && nb <= CAND_B_MAX && nb <= (uint64_t)n * wa && rank >= below + guard && rank + guard < below + total;
     if (!ok) {
         if (threadIdx.x == 0) *flag = 1;
         return;
     }
-    const uint64_t k = select_rank(w.cand + (size_t)ip * w.cand_cap, n, rank - below, &sc);
+    const uint64_t k = select_rank(w.cand + (size_t)ip * w.cand_cap, n, wa, w.cand_b + (size_t)ip * CAND_B_MAX, nb, rank - below, &sc);
     if (threadIdx.x == 0) median[ip] = __longlong_as_double((long long)k);
 }
 
@@ -612,7 +696,8 @@ __global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P,
 // Only the quarter-disc y,x <= rhi can satisfy the radius test, so only that box is scanned.
 __global__ void __launch_bounds__(256) capacity_count(const double2* __restrict__ spec, SpecLayout lay, int ymax, int xmax,
                                                       double rlo, double rhi, double magmin,
-                                                      const double* __restrict__ median, uint64_t* counts) {
+                                                      const double* __restrict__ median, uint64_t* counts, const int* gate) {
+    if (gate && !*gate) return;  // the fused count of the median scan stands
     const int ip = blockIdx.y;
     const int PH = lay.PH, PW = lay.PW;
     const double thr = magmin * median[ip];
@@ -649,20 +734,64 @@ __global__ void capacity_finish(const uint64_t* counts, uint64_t* usable, int ni
     if (i < nimg) usable[i] = counts[3 * i] / 2 + counts[3 * i + 1] / 2 + counts[3 * i + 2] / 2;  // S:1006, S:1008
 }
 
+// Fused capacity, step 2 (one warp per plane): settle the undecided annulus bins against the exact
+// threshold magmin*median (abs(F) < t, S:1004).  A plane whose list overflowed raises flags[1] and the
+// whole batch is recounted by capacity_count.
+__global__ void __launch_bounds__(128) capacity_resolve(MedianWork w, int nplanes, double magmin, const double* __restrict__ median,
+                                                        uint64_t ann_total) {
+    const int ip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (ip >= nplanes) return;
+    const uint32_t n = w.cap_unc_n[ip];
+    if (n > CAP_UNC_MAX) {
+        if (lane == 0) { w.flags[1] = 1; w.counts[ip] = 0; }
+        return;
+    }
+    const double thr = magmin * median[ip];
+    unsigned c = 0;
+    for (uint32_t i = lane; i < n; i += 32)
+        c += __longlong_as_double((long long)w.cap_unc[(size_t)ip * CAP_UNC_MAX + i]) < thr ? 1u : 0u;
+    for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if (lane == 0) w.counts[ip] = ann_total - w.cap_below[ip] - c;
+}
+__global__ void capacity_zero_gated(uint64_t* counts, int nplanes, const int* gate) {
+    if (!*gate) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nplanes) counts[i] = 0;
+}
+
+// number of off-axis bins inside the annulus (geometry only; the loop of count_plane S:999-1003 without the
+// magnitude test), cached per geometry
+static uint64_t annulus_total_host(int PH, int PW, int ymax, int xmax, double rlo, double rhi) {
+    struct Key { int PH, PW; double rlo, rhi; uint64_t n; };
+    static std::vector<Key> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const Key& k : cache)
+        if (k.PH == PH && k.PW == PW && k.rlo == rlo && k.rhi == rhi) return k.n;
+    uint64_t n = 0;
+    for (int y = 1; y <= ymax; y++) {
+        if (y == PH / 2) continue;
+        for (int x = 1; x <= xmax; x++) {
+            if (x == PW / 2) continue;
+            const double r = sqrt((double)((long long)y * y + (long long)x * x));
+            if (r >= rlo && r <= rhi) n++;
+        }
+    }
+    if (cache.size() > 64) cache.clear();
+    cache.push_back(Key{PH, PW, rlo, rhi, n});
+    return n;
+}
+
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
                                    double* d_median, uint64_t* d_usable) {
     const int PH = lay.PH, PW = lay.PW;
     const uint64_t P = (uint64_t)PH * PW;        // size of the full multiset (ranks refer to it)
     const uint64_t E = lay.plane_elems();        // stored elements per plane
-    const int chunks = (int)((E + 512ull * 16 - 1) / (512ull * 16));
-    const dim3 grid((unsigned)(chunks > 592 ? 592 : chunks), (unsigned)nplanes);
     median_init<<<(nplanes * RADIX + 255) / 256, 256, 0, L.stream>>>(w, nplanes, P);
     TFFT_LAUNCH_CHECK(L);
-    int* d_flag = (int*)(w.cand_n + nplanes);  // one spare word after cand_n (see median_work_bytes)
+    int* d_flag = w.flags;
     Bracket* br = (Bracket*)w.prefix2;
-    cudaError_t e = cudaMemsetAsync(d_flag, 0, sizeof(int), L.stream);
-    if (e != cudaSuccess) return e;
     const bool all = P <= (uint64_t)w.cand_cap && P <= (uint64_t)SAMPLE_MAX;  // small plane: everything is a member
     if (all) {
         median_bracket_all<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, nplanes, br);
@@ -676,9 +805,22 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, br);
         TFFT_LAUNCH_CHECK(L);
     }
-    median_scan<<<grid, 512, 0, L.stream>>>(spec, lay, w, br);
-    TFFT_LAUNCH_CHECK(L);
-    median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, d_median, d_flag, all ? 0u : RANK_GUARD);
+    int ymax = (int)floor(rhi), xmax = (int)floor(rhi);
+    if (ymax > PH - 1) ymax = PH - 1;
+    if (xmax > PW - 1) xmax = PW - 1;
+    if (ymax < 0) ymax = 0;
+    if (xmax < 0) xmax = 0;
+    // the capacity count rides on the scan when every annulus bin is a stored element (x <= rhi < PW/2 for a half plane)
+    ScanCap cap;
+    cap.on = (d_usable && !all && magmin >= 0.0 && (!lay.half || xmax < PW / 2)) ? 1 : 0;
+    cap.magmin2 = magmin * magmin; cap.rlo = rlo; cap.rhi = rhi;
+    {
+        const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
+        const unsigned per_plane = (unsigned)(ntiles < 296 ? ntiles : 296);
+        median_scan<<<dim3(per_plane, (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>(spec, lay, w, br, cap);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, lay.half ? 2u : 1u, d_median, d_flag, all ? 0u : RANK_GUARD);
     TFFT_LAUNCH_CHECK(L);
     // Fallback, decided on the device (no host sync): the generic radix passes are gated by the
     // flag and exit immediately in the normal case.
@@ -693,20 +835,27 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         median_from_prefix<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, d_median, nplanes, d_flag);
         TFFT_LAUNCH_CHECK(L);
     }
-    e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
-    if (e != cudaSuccess) return e;
     if (d_usable) {
-        int ymax = (int)floor(rhi), xmax = (int)floor(rhi);
-        if (ymax > PH - 1) ymax = PH - 1;
-        if (xmax > PW - 1) xmax = PW - 1;
-        if (ymax < 0) ymax = 0;
-        if (xmax < 0) xmax = 0;
         const long long box = (long long)(ymax + 1) * (xmax + 1);
         int cb = (int)((box + 256 * 8 - 1) / (256 * 8));
         if (cb > 1184) cb = 1184;
         if (cb < 1) cb = 1;
-        capacity_count<<<dim3((unsigned)cb, (unsigned)nplanes), 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts);
-        TFFT_LAUNCH_CHECK(L);
+        const dim3 cgrid((unsigned)cb, (unsigned)nplanes);
+        if (cap.on) {
+            const uint64_t ann = annulus_total_host(PH, PW, ymax, xmax, rlo, rhi);
+            capacity_resolve<<<(nplanes + 3) / 4, 128, 0, L.stream>>>(w, nplanes, magmin, d_median, ann);
+            TFFT_LAUNCH_CHECK(L);
+            capacity_zero_gated<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w.counts, nplanes, d_flag + 1);
+            TFFT_LAUNCH_CHECK(L);
+            // gated recount: almost never does real work, so keep the launch small (grid-stride loop inside)
+            capacity_count<<<dim3(cgrid.x < 16 ? cgrid.x : 16, cgrid.y), 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, d_flag + 1);
+            TFFT_LAUNCH_CHECK(L);
+        } else {
+            cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
+            if (e != cudaSuccess) return e;
+            capacity_count<<<cgrid, 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, nullptr);
+            TFFT_LAUNCH_CHECK(L);
+        }
         capacity_finish<<<(nplanes / 3 + 255) / 256, 256, 0, L.stream>>>(w.counts, d_usable, nplanes / 3);
         TFFT_LAUNCH_CHECK(L);
     }

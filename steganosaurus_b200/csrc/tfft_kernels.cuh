@@ -66,12 +66,23 @@ struct MedianWork {
     uint32_t* hist;      // [nplanes][2048]
     uint64_t* prefix;    // [nplanes] key prefix selected so far
     uint64_t* rank;      // [nplanes] remaining rank inside the prefix bucket
-    uint64_t* cand;      // [nplanes][cand_cap] candidate keys
+    uint64_t* cand;      // [nplanes][cand_cap] candidate keys (sample, then bracket members: each stored element once)
     uint32_t* cand_n;    // [nplanes]
     uint32_t cand_cap;
+    uint64_t* cand_b;    // [nplanes][CAND_B_MAX] members whose multiplicity is below the interior weight (edge / pad columns
+    uint32_t* cand_b_n;  // [nplanes]              of a half plane), one entry per unit of excess
     uint64_t* counts;    // [nplanes] below-bracket counts, then capacity counts before halving
     uint64_t* prefix2;   // [nplanes][2] median bracket (qlo, qhi as doubles)
+    // capacity fused into the median scan: annulus bins certainly below magmin*median are counted,
+    // the few whose verdict needs the exact median are staged (keys) and resolved afterwards
+    uint64_t* cap_below; // [nplanes]
+    uint64_t* cap_unc;   // [nplanes][CAP_UNC_MAX] keys of undecided annulus bins
+    uint32_t* cap_unc_n; // [nplanes]
+    uint64_t* ann_total; // [1] number of off-axis annulus bins of the geometry
+    int* flags;          // [0] median fallback, [1] capacity fallback
 };
+constexpr uint32_t CAP_UNC_MAX = 1024;
+constexpr uint32_t CAND_B_MAX = 1u << 15;
 size_t median_work_bytes(int nplanes, uint32_t cand_cap);
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);
 // d_median: [nplanes]; d_usable: [nplanes/3] (sum over the 3 planes of count/2)

@@ -190,7 +190,8 @@ template <int R1>
 __device__ __forceinline__ int swz(int k1, int k2, int low) { return (k1 << 8) | (k2 << 4) | (low ^ ((k1 + R1 * k2) & 15)); }
 
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
-template <int S, int LOG2N, int VEC, bool FROM_U8>
+// NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
+template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256>
 __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
                                        const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/,
                                        const double2* w1pre /*per-thread constants hoisted by the caller when J1 <= 2*/) {
@@ -210,7 +211,7 @@ __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2*
                 }
                 x[n] = make_double2(v, 0.0);
             } else {
-                x[n] = L[(n * 256 + m) * VEC + c];
+                x[n] = n < NZ ? L[(n * 256 + m) * VEC + c] : make_double2(0.0, 0.0);
             }
         }
         dft<S, G::R1>(x);
@@ -475,7 +476,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
                  ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <int S>
+// NZ : only the first NZ 256-row blocks of the input are non-zero (forward pass of a padded image): the
+//      other boxes are neither loaded nor read, and stage 1 folds the zero butterflies away.
+// K3N: only the first K3N 256-row blocks of the output are kept (inverse pass before the crop): the
+//      other results are neither computed (dead code) nor staged.
+template <int S, int NZ, int K3N>
 __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant__ CUtensorMap in_map,
                                                            const __grid_constant__ CUtensorMap out_map, ColTmaArgs a) {
     constexpr int LOG2N = 12, VEC = 2;
@@ -499,11 +504,12 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     }
     __syncthreads();
 
+    static_assert(NZ >= 1 && NZ <= NBOX && K3N >= 1 && K3N <= 16, "block counts");
     auto issue_load = [&](long long it) {
         const int plane = (int)(it / a.groups_per_plane), g = (int)(it % a.groups_per_plane);
-        mbar_expect_tx(&full_bar, (unsigned)G::L_BYTES);
+        mbar_expect_tx(&full_bar, (unsigned)((size_t)NZ * BOX_ROWS * VEC * 16));
 #pragma unroll 1
-        for (int j = 0; j < NBOX; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
+        for (int j = 0; j < NZ; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
     };
 
     const long long stride = gridDim.x;
@@ -513,7 +519,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     for (; item < a.nitems; item += stride) {
         mbar_wait(&full_bar, parity);
         parity ^= 1;
-        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
+        stage1<S, LOG2N, VEC, false, NZ>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
         __syncthreads();
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
@@ -541,11 +547,12 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         dft<S, 16>(z);  // z[oidx(k3)] = output row k1 + 16*m + 256*k3 of column c
         const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int h = 0; h < (K3N > 8 ? 2 : 1); h++) {
             if (h == 1) __syncthreads();  // the first half has been read out by the TMA engine
             __syncwarp();                 // every lane is past its reads of the slice
 #pragma unroll
             for (int k3 = 8 * h; k3 < 8 * h + 8; k3++) {
+                if (k3 >= K3N) continue;  // rows the store map clips anyway
                 double2 v = z[oidx<16>(k3)];
                 v.x *= scale; v.y *= scale;
                 Sw[((k3 - 8 * h) * 16 + m) * VEC + c] = v;
@@ -1041,7 +1048,7 @@ bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int P
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int S>
+template <int S, int NZ, int K3N>
 cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     using G = pk::Geo<12, 2>;
     CUtensorMap in_map, out_map;
@@ -1051,7 +1058,7 @@ cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     pk::ColTmaArgs a;
     a.tw = p.tw; a.groups_per_plane = p.PW / 2; a.nitems = (long long)p.nplanes * a.groups_per_plane;
     const size_t smem = G::L_BYTES + G::X_BYTES;
-    auto kern = pk::pencil_col_tma_w<S>;
+    auto kern = pk::pencil_col_tma_w<S, NZ, K3N>;
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, a);
@@ -1149,7 +1156,10 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
         static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
         if (L.fft_impl != 2 && !blockk && p.PW >= 2) {
             bool ok = false;
-            cudaError_t e = p.inverse ? run_col_tma_w<-1>(L, p, &ok) : run_col_tma_w<+1>(L, p, &ok);
+            // zero structure of a padded image (UHD: 2160 of 4096 rows): 9 of 16 row blocks carry data
+            const bool few_in = p.in_rows <= 9 * 256, few_out = p.out_rows <= 9 * 256;
+            cudaError_t e = p.inverse ? (few_out ? run_col_tma_w<-1, 16, 9>(L, p, &ok) : run_col_tma_w<-1, 16, 16>(L, p, &ok))
+                                      : (few_in ? run_col_tma_w<+1, 9, 16>(L, p, &ok) : run_col_tma_w<+1, 16, 16>(L, p, &ok));
             if (e != cudaSuccess || ok) return e;
         }
     }
