@@ -189,6 +189,24 @@ enum Mode { M_C2C_ROW = 0, M_C2C_COL = 1, M_U8_FWD = 2, M_U8_INV = 3 };
 template <int R1>
 __device__ __forceinline__ int swz(int k1, int k2, int low) { return (k1 << 8) | (k2 << 4) | (low ^ ((k1 + R1 * k2) & 15)); }
 
+// Exchange-2 position used by the fused u8 row kernels.  N = 4096 (R1 = 16): every 256 entries are padded by
+// one (row stride 257), which keeps the stride-16 writers and the stride-256 readers conflict-free AND gives
+// every access a compile-time offset from one per-thread base (the XOR swizzle costs two integer
+// instructions per access; these kernels are issue-bound).  Smaller N keep the XOR swizzle.
+template <int R1>
+__device__ __forceinline__ int xpos(int k1, int k2, int low) {
+    if constexpr (R1 == 16) return k1 * 257 + (k2 << 4) + low;
+    else return swz<R1>(k1, k2, low);
+}
+template <int LOG2N>
+constexpr int xpad() { return LOG2N == 12 ? 16 : 0; }  // extra entries of a padded exchange buffer
+
+__device__ __forceinline__ unsigned lds_u8(unsigned saddr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
 template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256>
@@ -281,18 +299,26 @@ __device__ __forceinline__ void stage23(double* X, int tt, int c, double2 w1, do
 
 // Variant for passes whose L buffer is not a landing buffer (u8 forward rows): exchange 2 runs in
 // place in L with 16 B entries and the same XOR swizzle -> one barrier instead of three.
-template <int S, int LOG2N>
+template <int S, int LOG2N, bool PADDED = false>
 __device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, double2* x, int bar_id) {
     using G = Geo<LOG2N, 1>;
     const int k1 = tt >> 4, m = tt & 15;
     dft<S, 16>(x);
     twiddle<16>(x, w1);
     const int k1r = tt & (G::R1 - 1), k2r = tt / G::R1;
+    [[maybe_unused]] double2* Lw = L + xpos<G::R1>(k1, 0, m);   // R1 == 16: the 16 accesses are Lw[16 k2] / Lr[n] (immediate offsets)
+    [[maybe_unused]] const double2* Lr = L + xpos<G::R1>(k1r, k2r, 0);
 #pragma unroll
-    for (int k2 = 0; k2 < 16; k2++) L[swz<G::R1>(k1, k2, m)] = x[oidx<16>(k2)];
+    for (int k2 = 0; k2 < 16; k2++) {
+        if constexpr (PADDED && G::R1 == 16) Lw[k2 << 4] = x[oidx<16>(k2)];
+        else L[(PADDED ? xpos<G::R1>(k1, k2, m) : swz<G::R1>(k1, k2, m))] = x[oidx<16>(k2)];
+    }
     unit_bar(bar_id, G::UT);
 #pragma unroll
-    for (int n = 0; n < 16; n++) x[n] = L[swz<G::R1>(k1r, k2r, n)];
+    for (int n = 0; n < 16; n++) {
+        if constexpr (PADDED && G::R1 == 16) x[n] = Lr[n];
+        else x[n] = L[(PADDED ? xpos<G::R1>(k1r, k2r, n) : swz<G::R1>(k1r, k2r, n))];
+    }
     dft<S, 16>(x);
 }
 
@@ -751,22 +777,34 @@ struct R2CArgs {
 };
 
 // ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
-template <int LOG2N, int UNITS>
+// Staging of a row pair: each row has its own zero-padded region of RS = 3N + 32 bytes, filled by a FIXED
+// number of 16 B cp.async chunks (source size 0 beyond the row end -> zero fill), so stage 1 reads pixel
+// x < N without any bounds test and an absent second row (odd H) is simply all zeros.
+template <int LOG2N>
+struct R2CGeo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr size_t RS = (size_t)N * 3 + 32;                        // staging bytes per row
+    static constexpr size_t UB = 2 * RS;                                    // per buffer (row pair)
+    static constexpr size_t LF_BYTES = (size_t)(N + xpad<LOG2N>()) * 16;    // forward: L with padded exchange 2
+    static constexpr size_t FWD_UNIT = LF_BYTES + 2 * UB;
+};
+
+template <int LOG2N, int UNITS, bool CENTER>
 __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c(R2CArgs a) {
     using G = Geo<LOG2N, 1>;
+    using RG = R2CGeo<LOG2N>;
     constexpr int N = G::N, NH = N / 2;
-    constexpr size_t UB = (size_t)2 * N * 3 + 32;  // aligned span of two adjacent RGB rows
-    constexpr size_t UNIT_BYTES = G::L_BYTES + 2 * UB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
-    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    unsigned char* base = smem_raw + (size_t)unit * RG::FWD_UNIT;
     double2* L = (double2*)base;
-    unsigned char* U[2] = {base + G::L_BYTES, base + G::L_BYTES + UB};
+    unsigned char* Ub = base + RG::LF_BYTES;            // two row-pair buffers of UB bytes
     const int bar_id = 1 + unit;
     const long long stride = (long long)gridDim.x * UNITS;
     long long item = (long long)blockIdx.x * UNITS + unit;
     const int HP = (a.H + 1) / 2;  // row pairs per image
     const size_t row_bytes = (size_t)a.W * 3;
+    const int nch = (int)((row_bytes + 15) >> 4) + 1;   // chunks per row: covers every 16 B phase of the row start
     const uintptr_t img_base = (uintptr_t)a.img_in;
     ThreadTw<+1, LOG2N, 1> ttw;
     ttw.load(a.tw, tt);
@@ -777,36 +815,44 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         return img_base + ((size_t)img * a.H + y0) * row_bytes;
     };
     auto pair_rows = [&](long long it) -> int { return (2 * (int)(it % HP) + 1 < a.H) ? 2 : 1; };
-    auto issue_rows = [&](long long it, unsigned char* dst) {
-        const uintptr_t start = pair_start(it);
-        const size_t nbytes = row_bytes * pair_rows(it);
-        const uintptr_t a0 = start & ~(uintptr_t)15;
-        const int nchunks = (int)((start + nbytes - a0 + 15) >> 4);
-        const uintptr_t end = start + nbytes;  // never read past the pair (the next bytes may not exist)
-        for (int i = tt; i < nchunks; i += G::UT) {
-            const uintptr_t src = a0 + (size_t)i * 16;
-            long long avail = (long long)(end - src);
-            int nb = avail >= 16 ? 16 : (avail > 0 ? (int)avail : 0);
-            cp_async16(dst + (size_t)i * 16, (const void*)(nb ? src : img_base), nb);
+    auto issue_rows = [&](long long it, int buf) {
+        const uintptr_t s0 = pair_start(it);
+        const int nrows = pair_rows(it);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uintptr_t start = s0 + (size_t)r * row_bytes;
+            const unsigned char* a0 = (const unsigned char*)(start & ~(uintptr_t)15);
+            const int span = r < nrows ? (int)(start & 15) + (int)row_bytes : 0;  // bytes from a0 to the row end; absent row: all zero-fill
+            unsigned char* dst = Ub + (size_t)buf * RG::UB + (size_t)r * RG::RS;
+            for (int i = tt; i < nch; i += G::UT) {
+                const int avail = span - i * 16;
+                const int nb = avail >= 16 ? 16 : (avail > 0 ? avail : 0);
+                cp_async16(dst + i * 16, a0 + i * 16, nb);  // nb == 0: nothing is read (pure zero fill)
+            }
         }
         cp_async_commit();
     };
 
+    // zero the staging tails once (bytes beyond the chunks are never written again)
+    for (size_t i = (size_t)tt * 16; i < 2 * RG::UB; i += (size_t)G::UT * 16) *(uint4*)(Ub + i) = make_uint4(0, 0, 0, 0);
     if (unit & 1) {
         const long long t0 = clock64();
         while (clock64() - t0 < STAGGER_CYCLES) {}
     }
+    unit_bar(bar_id, G::UT);
     int buf = 0;
-    if (item < a.nitems) issue_rows(item, U[0]);
+    if (item < a.nitems) issue_rows(item, 0);
     for (; item < a.nitems; item += stride, buf ^= 1) {
         cp_async_wait_all();
         unit_bar(bar_id, G::UT);
-        if (item + stride < a.nitems) issue_rows(item + stride, U[buf ^ 1]);
+        if (item + stride < a.nitems) issue_rows(item + stride, buf ^ 1);
         const long long img = item / HP;
         const int y0 = 2 * (int)(item % HP);
         const int nrows = pair_rows(item);
-        const uint8_t* r0 = U[buf] + (pair_start(item) & 15);
-        const uint8_t* r1 = r0 + row_bytes;
+        const uintptr_t s0 = pair_start(item);
+        // shared-space byte addresses of pixel tt of row 0 / row 1 (channel 0)
+        const uint8_t* r0 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + (s0 & 15) + (size_t)tt * 3;
+        const uint8_t* r1 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + row_bytes) & 15) + (size_t)tt * 3;
         for (int ch = 0; ch < 3; ch++) {
             // ---- stage 1 on z = row0 + i*row1 (plane split, centre sign, zero pad fused; S:383-398)
 #pragma unroll
@@ -815,14 +861,10 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                 double2 x[G::R1];
 #pragma unroll
                 for (int n = 0; n < G::R1; n++) {
-                    const int xc = n * 256 + m;
-                    double v0 = 0.0, v1 = 0.0;
-                    if (xc < a.W) {
-                        v0 = (double)r0[xc * 3 + ch];
-                        if (nrows == 2) v1 = (double)r1[xc * 3 + ch];
-                        if (a.center) {  // apply_center S:392: (-1)^(x+y)
-                            if ((xc + y0) & 1) v0 = -v0; else v1 = -v1;
-                        }
+                    const unsigned o = (unsigned)((n * 256 + j * G::TP) * 3) + (unsigned)ch;
+                    double v0 = (double)r0[o], v1 = (double)r1[o];
+                    if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); x parity == m parity
+                        if ((m + y0) & 1) v0 = -v0; else v1 = -v1;
                     }
                     x[n] = make_double2(v0, v1);
                 }
@@ -836,19 +878,21 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
             double2 x[16];
             stage2_load<LOG2N, 1>(L, tt, 0, x);
             unit_bar(bar_id, G::UT);
-            stage23_inplace<+1, LOG2N>(L, tt, ttw.s2v(), x, bar_id);  // x[oidx(k3)] = Z[tt + TP*k3]
-            unit_bar(bar_id, G::UT);                                  // all reads of L done
+            stage23_inplace<+1, LOG2N, true>(L, tt, ttw.s2v(), x, bar_id);  // x[oidx(k3)] = Z[tt + TP*k3]
+            unit_bar(bar_id, G::UT);                                        // all reads of L done
             // ---- split Z into the spectra of the two real rows: partners Z[N-k] through L
 #pragma unroll
             for (int k3 = 8; k3 < 16; k3++) L[tt + G::TP * (k3 - 8)] = x[oidx<16>(k3)];  // Z[N/2 + j] at L[j]
+            if (tt == 0) L[NH] = x[oidx<16>(0)];                                          // Z[0] is its own partner
             unit_bar(bar_id, G::UT);
             double2* out0 = a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
             double2* out1 = out0 + a.ld;
+            const double2* Lp = L + NH - tt;
 #pragma unroll
             for (int k3 = 0; k3 < 8; k3++) {
                 const int k = tt + G::TP * k3;
                 const double2 z = x[oidx<16>(k3)];
-                const double2 zn = (k == 0) ? z : L[NH - k];  // Z[N-k] = L[(N-k) - N/2]
+                const double2 zn = Lp[-G::TP * k3];  // Z[N-k] = L[(N-k) - N/2]; k = 0 reads L[NH] = Z[0]
                 out0[k] = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));            // (Z[k] + conj Z[N-k]) / 2
                 if (nrows == 2) out1[k] = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));  // (Z[k] - conj Z[N-k]) / 2i
             }
@@ -863,17 +907,69 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
 }
 
 // ---- inverse: 2 x 3 half-spectrum rows -> two u8 rows (C2R + scale/crop/centre/round/clamp) ----
-template <int LOG2N, int UNITS>
+// from_planes_u8's clamp8 (S:389): (uint8_t)max(0, min(255, round(v))) with round() = half away from zero.
+// For v >= 0, round(v) == trunc(v + pred(0.5)) exactly (pred(0.5) = 0.5 - 2^-54: a tie still rounds up to the
+// next integer, anything below the tie cannot reach it); negative v clamp to 0 and the unsigned conversion
+// saturates them (and NaN) to 0.  Three instructions instead of round/min/max/cast.
+__device__ __forceinline__ uint8_t clamp8_fast(double v) {
+    const unsigned u = __double2uint_rz(v + 0.49999999999999994);
+    return (uint8_t)min(u, 255u);
+}
+
+// stage 2 + exchange 2 through the split re/im buffer X (8 B entries, xpos layout) + stage 3, VEC = 1
+template <int S, int LOG2N>
+__device__ __forceinline__ void stage23_x(double* X, int tt, double2 w1, double2* x, int bar_id) {
+    using G = Geo<LOG2N, 1>;
+    constexpr bool PD = G::R1 == 16;
+    const int k1 = tt >> 4, m = tt & 15;
+    dft<S, 16>(x);
+    twiddle<16>(x, w1);
+    const int k1r = tt & (G::R1 - 1), k2r = tt / G::R1;
+    [[maybe_unused]] double* Xw = X + xpos<G::R1>(k1, 0, m);
+    [[maybe_unused]] const double* Xr = X + xpos<G::R1>(k1r, k2r, 0);
+    double2 z[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) {
+        if constexpr (PD) Xw[k2 << 4] = x[oidx<16>(k2)].x; else X[xpos<G::R1>(k1, k2, m)] = x[oidx<16>(k2)].x;
+    }
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        if constexpr (PD) z[n].x = Xr[n]; else z[n].x = X[xpos<G::R1>(k1r, k2r, n)];
+    }
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; k2++) {
+        if constexpr (PD) Xw[k2 << 4] = x[oidx<16>(k2)].y; else X[xpos<G::R1>(k1, k2, m)] = x[oidx<16>(k2)].y;
+    }
+    unit_bar(bar_id, G::UT);
+#pragma unroll
+    for (int n = 0; n < 16; n++) {
+        if constexpr (PD) z[n].y = Xr[n]; else z[n].y = X[xpos<G::R1>(k1r, k2r, n)];
+    }
+    dft<S, 16>(z);
+#pragma unroll
+    for (int n = 0; n < 16; n++) x[n] = z[n];
+}
+
+template <int LOG2N>
+struct C2RGeo {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr size_t LB = (size_t)(N + 2) * 16 + 32;              // landing: A half then B half; exchange 1 reuses [0,N)
+    static constexpr size_t XB = (size_t)(N + xpad<LOG2N>()) * 8;        // split exchange-2 buffer
+    static constexpr size_t UNIT = LB + ((XB + 15) & ~(size_t)15);
+};
+
+template <int LOG2N, int UNITS, bool CENTER>
 __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r(R2CArgs a) {
     using G = Geo<LOG2N, 1>;
+    using CG = C2RGeo<LOG2N>;
     constexpr int N = G::N, NH = N / 2, HL = NH + 1;  // HL entries per half row
-    constexpr size_t LB = (size_t)(N + 2) * 16 + 32;  // landing: A half then B half; exchange 1 reuses [0,N)
-    constexpr size_t UNIT_BYTES = LB + G::X_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
-    unsigned char* base = smem_raw + (size_t)unit * UNIT_BYTES;
+    unsigned char* base = smem_raw + (size_t)unit * CG::UNIT;
     double2* L = (double2*)base;
-    double* X = (double*)(base + LB);
+    double* X = (double*)(base + CG::LB);
     const int bar_id = 1 + unit;
     const long long stride = (long long)gridDim.x * UNITS;
     long long item = (long long)blockIdx.x * UNITS + unit;
@@ -909,25 +1005,31 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
         const long long img = item / HP;
         const int y0 = 2 * (int)(item % HP);
         const bool two = y0 + 1 < a.H;
-        uint8_t* o0 = a.img_out + ((size_t)img * a.H + y0) * row_bytes;
+        uint8_t* o0 = a.img_out + ((size_t)img * a.H + y0) * row_bytes + (size_t)tt * 3;
         uint8_t* o1 = o0 + row_bytes;
         for (int ch = 0; ch < 3; ch++) {
             cp_async_wait_all();
             unit_bar(bar_id, G::UT);
-            // ---- gather Z[k] = A[k] + i B[k] (k <= N/2) or conj(A[N-k]) + i conj(B[N-k]) (k > N/2)
+            // ---- gather Z[k] = A[k] + i B[k] (k <= N/2) or conj(A[N-k]) + i conj(B[N-k]) (k > N/2); k = 256 n + m:
+            // blocks n < R1/2 take the first form, n > R1/2 the second, block R1/2 the first only at k = N/2 (m = 0)
             double2 x[16];
 #pragma unroll
             for (int j = 0; j < G::J1; j++) {
                 const int m = tt + j * G::TP;
+                const double2* Lf = L + m;        // form 1: A = Lf[256 n], B = Lf[HL + 256 n]
+                const double2* Lb = L + N - m;    // form 2: A = Lb[-256 n], B = Lb[HL - 256 n]
+                const double smid = (m == 0) ? 1.0 : -1.0;
 #pragma unroll
                 for (int n = 0; n < G::R1; n++) {
-                    const int k = n * 256 + m;
-                    if (k <= NH) {
-                        const double2 A = L[k], B = L[HL + k];
+                    if (n < G::R1 / 2) {
+                        const double2 A = Lf[256 * n], B = Lf[HL + 256 * n];
                         x[j * G::R1 + n] = make_double2(A.x - B.y, A.y + B.x);
-                    } else {
-                        const double2 A = L[N - k], B = L[HL + N - k];
+                    } else if (n > G::R1 / 2) {
+                        const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
                         x[j * G::R1 + n] = make_double2(A.x + B.y, B.x - A.y);
+                    } else {  // k = N/2 + m: element N/2 - m of both halves; m = 0 is the Nyquist bin itself (first form)
+                        const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
+                        x[j * G::R1 + n] = make_double2(fma(-smid, B.y, A.x), fma(smid, A.y, B.x));
                     }
                 }
             }
@@ -948,18 +1050,18 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
             unit_bar(bar_id, G::UT);  // L is free: prefetch the next plane / the next item's first plane
             if (ch < 2) issue_loads(item, ch + 1);
             else if (item + stride < a.nitems) issue_loads(item + stride, 0);
-            stage23<-1, LOG2N, 1>(X, tt, 0, ttw.s2v(), x, bar_id);
+            stage23_x<-1, LOG2N>(X, tt, ttw.s2v(), x, bar_id);
             // ---- epilogue (ifft_crop S:399, apply_center S:1102, from_planes_u8 S:387): Re -> row y0, Im -> row y0+1
 #pragma unroll
             for (int k3 = 0; k3 < 16; k3++) {
                 const int k = tt + G::TP * k3;
                 if (k < a.W) {
                     double v0 = x[oidx<16>(k3)].x * scale, v1 = x[oidx<16>(k3)].y * scale;
-                    if (a.center) {
+                    if constexpr (CENTER) {
                         if ((k + y0) & 1) v0 = -v0; else v1 = -v1;
                     }
-                    o0[(size_t)k * 3 + ch] = clamp8(v0);
-                    if (two) o1[(size_t)k * 3 + ch] = clamp8(v1);
+                    o0[G::TP * k3 * 3 + ch] = clamp8_fast(v0);
+                    if (two) o1[G::TP * k3 * 3 + ch] = clamp8_fast(v1);
                 }
             }
         }
@@ -1107,26 +1209,31 @@ cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
     return cudaGetLastError();
 }
 
-template <int LOG2N, int UNITS, bool INV>
-cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
+template <int LOG2N, int UNITS, bool INV, bool CENTER>
+cudaError_t run_r2c_c(const Launcher& L, const pk::R2CArgs& a) {
     using G = pk::Geo<LOG2N, 1>;
-    pk::R2CArgs a;
-    a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
-    a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
-    a.nitems = (long long)(p.nplanes / 3) * ((p.H + 1) / 2);
-    const size_t smem = (INV ? ((size_t)(G::N + 2) * 16 + 32 + G::X_BYTES) : (G::L_BYTES + 2 * ((size_t)2 * G::N * 3 + 32))) * UNITS;
+    const size_t smem = (INV ? pk::C2RGeo<LOG2N>::UNIT : pk::R2CGeo<LOG2N>::FWD_UNIT) * UNITS;
     cudaError_t e;
     if constexpr (INV) {
-        auto kern = pk::pencil_u8_inv_c2r<LOG2N, UNITS>;
+        auto kern = pk::pencil_u8_inv_c2r<LOG2N, UNITS, CENTER>;
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     } else {
-        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS>;
+        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS, CENTER>;
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     }
     if (L.launch_counter) ++*L.launch_counter;
     return cudaGetLastError();
+}
+
+template <int LOG2N, int UNITS, bool INV>
+cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
+    pk::R2CArgs a;
+    a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
+    a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
+    a.nitems = (long long)(p.nplanes / 3) * ((p.H + 1) / 2);
+    return p.center ? run_r2c_c<LOG2N, UNITS, INV, true>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false>(L, a);
 }
 
 // per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB

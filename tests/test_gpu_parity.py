@@ -93,7 +93,9 @@ def test_golden_embed_extract(ctx, name):
     (256, 256, 2480, False, 0.5), (512, 512, 60000, False, 0.5), (500, 300, 5000, True, 0.3),
     (1024, 512, 30000, False, 0.18), (640, 480, 8000, False, 0.5), (1100, 600, 20000, True, 0.5),
     (2048, 1024, 50000, False, 0.5), (513, 1025, 9000, False, 0.5), (3000, 200, 4000, False, 0.5),
-    (5000, 300, 6000, False, 0.5), (700, 9000, 6000, True, 0.5)])
+    (5000, 300, 6000, False, 0.5), (700, 9000, 6000, True, 0.5),
+    # 4096-point fused u8 row kernels (R2C / C2R): ragged row bytes, odd H (half-empty last pair), centre on and off
+    (3001, 601, 7000, True, 0.5), (2500, 520, 7000, False, 0.5), (4096, 513, 7000, True, 0.5)])
 def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
     o = oracle()
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
