@@ -249,6 +249,10 @@ def run_ours(args):
         arm.close()
         cpu_base = arm.describe(arm.workers * W * H / 1e6 / t)
 
+    # host placement (after the CPU baseline, which uses every core): CPU time and pinned staging on the GPU's NUMA node
+    from steganosaurus_b200 import shard as _shard
+    placement = _shard.bind_host_to_gpu(local_rank) if os.environ.get("TFFT_NO_NUMA_BIND") is None else {"numa_node": None}
+
     # ---- synthetic workload (seeded)
     # the real keyed turtlewalk (host C++, ~1.7 s for 1.72 M bins at 4096^2; cover-independent, shared by the batch)
     from steganosaurus_b200 import host
@@ -364,7 +368,8 @@ def run_ours(args):
                                f"({nbits} bits, one shared bin list), embed+extract", "images_per_gpu_per_step": B,
                    "l2": f"inputs larger than L2 ({B * img_bytes / 1e9:.1f} GB covers + {3 * PW * PH * 16 / 1e9:.2f} GB spectra per image)",
                    "fft_impl": os.environ.get("TFFT_FFT_IMPL", "default"), "usable_min_bits": usable_min,
-                   "stego_pixels_changed": round(changed, 4), "bins": "keyed turtlewalk (host), density 0.7"},
+                   "stego_pixels_changed": round(changed, 4), "bins": "keyed turtlewalk (host), density 0.7",
+                   "host_placement": placement},
         "clocks": clocks,
         "e2e": {"value": world * mp_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None,

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libtfft_b200.so")
+LIB_PATH = os.environ.get("TFFT_LIB") or os.path.join(PKG, "libtfft_b200.so")  # TFFT_LIB: experiment builds of the same CUDA library
 
 # every symbol include/tfft.h declares
 SYMBOLS = [

@@ -33,7 +33,8 @@ struct Slot {
 
 }  // namespace
 
-constexpr int NSLOT = 3;  // host pipeline depth: H2D of chunk i+1, kernels of chunk i, D2H of chunk i-1 overlap
+constexpr int NSLOT = 8;   // slots allocated per context
+static int HOST_SLOTS = 4;  // host pipeline depth in use (TFFT_HOST_SLOTS): H2D of later chunks, kernels, D2H of earlier chunks overlap
 
 struct tfft_ctx {
     int device = 0;
@@ -370,6 +371,7 @@ int tfft_create(int device, tfft_ctx** out) {
     const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
     ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
     if (const char* hc = getenv("TFFT_HOST_CHUNK")) { int v = atoi(hc); if (v >= 1 && v <= MAX_CHUNK) HOST_CHUNK = v; }
+    if (const char* hs = getenv("TFFT_HOST_SLOTS")) { int v = atoi(hs); if (v >= 1 && v <= NSLOT) HOST_SLOTS = v; }
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
     for (int i = 0; i < NSLOT; i++)
@@ -470,8 +472,8 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = std::min(chunk_for(ctx, g, n, NSLOT), HOST_CHUNK);
-    const int nslots = std::min(NSLOT, (n + chunk - 1) / chunk);
+    const int chunk = std::min(chunk_for(ctx, g, n, HOST_SLOTS), HOST_CHUNK);
+    const int nslots = std::min(HOST_SLOTS, (n + chunk - 1) / chunk);
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
@@ -558,8 +560,8 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    const int chunk = std::min(chunk_for(ctx, g, n, NSLOT), HOST_CHUNK);
-    const int nslots = std::min(NSLOT, (n + chunk - 1) / chunk);
+    const int chunk = std::min(chunk_for(ctx, g, n, HOST_SLOTS), HOST_CHUNK);
+    const int nslots = std::min(HOST_SLOTS, (n + chunk - 1) / chunk);
     const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
     const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
     // header bytes and payload bytes share one device buffer per slot: [chunk][nb] then [chunk][nbp]

@@ -4,6 +4,7 @@
 #include "tfft_kernels.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 
@@ -408,7 +409,13 @@ __device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     // min / max
     uint64_t mn = ~0ull, mx = 0;
-    for (uint32_t i = tid; i < n; i += blockDim.x) { const uint64_t k = c[i]; mn = k < mn ? k : mn; mx = k > mx ? k : mx; }
+    for (uint32_t i0 = tid; i0 < n; i0 += blockDim.x * 8) {
+        uint64_t k[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) k[u] = (i0 + u * blockDim.x < n) ? c[i0 + u * blockDim.x] : c[tid < n ? tid : 0];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { mn = k[u] < mn ? k[u] : mn; mx = k[u] > mx ? k[u] : mx; }
+    }
     for (int o = 16; o; o >>= 1) {
         const uint64_t a = __shfl_xor_sync(0xffffffffu, mn, o), b2 = __shfl_xor_sync(0xffffffffu, mx, o);
         mn = a < mn ? a : mn; mx = b2 > mx ? b2 : mx;
@@ -430,9 +437,14 @@ __device__ uint64_t select_rank(const uint64_t* __restrict__ c, uint32_t n, uint
         const uint64_t prefix = sc->prefix;
         for (int i = tid; i < RADIX; i += blockDim.x) sc->hist[i] = 0;
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const uint64_t k = c[i];
-            if (top == 64 || (k >> top) == (prefix >> top)) atomicAdd(&sc->hist[(unsigned)(k >> sft) & ((1u << wid) - 1)], wa);
+        for (uint32_t i0 = tid; i0 < n; i0 += blockDim.x * 8) {
+            uint64_t k[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) k[u] = (i0 + u * blockDim.x < n) ? c[i0 + u * blockDim.x] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (i0 + u * blockDim.x < n && (top == 64 || (k[u] >> top) == (prefix >> top)))
+                    atomicAdd(&sc->hist[(unsigned)(k[u] >> sft) & ((1u << wid) - 1)], wa);
         }
         __syncthreads();  // every +wa lands before the -1 of the same key: bins never go negative
         for (uint32_t i = tid; i < nb; i += blockDim.x) {
@@ -504,7 +516,21 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
     if (rhi > (long long)S - 1) rhi = S - 1;
     for (int i = threadIdx.x; i < RADIX; i += blockDim.x) { h1[i] = 0; h2lo[i] = 0; h2hi[i] = 0; }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) atomicAdd(&h1[(unsigned)(c[i] >> 52) & (RADIX - 1)], 1u);
+    // level 1 = the 11 exponent bits: a spectrum lives in a handful of binades, so the increments of a warp are
+    // aggregated per distinct bin (match_any) instead of serialising on the same few counters; loads are
+    // batched 8 deep (the sample comes from L2)
+    for (uint32_t i0 = threadIdx.x; i0 < S; i0 += blockDim.x * 8) {
+        uint64_t k[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) k[u] = (i0 + u * blockDim.x < S) ? c[i0 + u * blockDim.x] : ~0ull;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const bool live = i0 + u * blockDim.x < S;
+            const unsigned bin = live ? (unsigned)(k[u] >> 52) & (RADIX - 1) : 0xffffffffu;
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (live && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h1[bin], (unsigned)__popc(peers));
+        }
+    }
     __syncthreads();
     if (threadIdx.x < 2) {  // thread 0: lower rank, thread 1: upper rank
         uint32_t r = threadIdx.x == 0 ? (uint32_t)rlo : (uint32_t)rhi;
@@ -514,11 +540,17 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
     }
     __syncthreads();
     const uint32_t blo = s_blo, bhi = s_bhi;
-    for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-        const uint64_t k = c[i];
-        const uint32_t top = (unsigned)(k >> 52) & (RADIX - 1), sub = (unsigned)(k >> 41) & (RADIX - 1);
-        if (top == blo) atomicAdd(&h2lo[sub], 1u);
-        if (top == bhi) atomicAdd(&h2hi[sub], 1u);
+    for (uint32_t i0 = threadIdx.x; i0 < S; i0 += blockDim.x * 8) {
+        uint64_t k[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) k[u] = (i0 + u * blockDim.x < S) ? c[i0 + u * blockDim.x] : ~0ull;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (i0 + u * blockDim.x >= S) continue;
+            const uint32_t top = (unsigned)(k[u] >> 52) & (RADIX - 1), sub = (unsigned)(k[u] >> 41) & (RADIX - 1);
+            if (top == blo) atomicAdd(&h2lo[sub], 1u);
+            if (top == bhi) atomicAdd(&h2hi[sub], 1u);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 2) {
@@ -816,7 +848,9 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     cap.magmin2 = magmin * magmin; cap.rlo = rlo; cap.rhi = rhi;
     {
         const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
-        const unsigned per_plane = (unsigned)(ntiles < 296 ? ntiles : 296);
+        static const unsigned cap_ctas = getenv("TFFT_SCAN_CTAS") ? (unsigned)atoi(getenv("TFFT_SCAN_CTAS")) : 296u;  // experiment switch
+        const unsigned cc = cap_ctas ? cap_ctas : 296u;
+        const unsigned per_plane = (unsigned)(ntiles < cc ? ntiles : cc);
         median_scan<<<dim3(per_plane, (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>(spec, lay, w, br, cap);
         TFFT_LAUNCH_CHECK(L);
     }

@@ -71,6 +71,9 @@ __device__ __host__ constexpr int oidx(int k) {
 
 template <int S, int R>
 __device__ __forceinline__ void dft(double2* x) {
+#ifdef TFFT_EXP_NO_FP64  // timing experiment only (results are garbage): data movement and barriers without the butterflies
+    return;
+#endif
     if constexpr (R == 2) {
         const double2 a = x[0], b = x[1];
         x[0] = cadd(a, b); x[1] = csub(a, b);
@@ -111,6 +114,10 @@ __device__ __forceinline__ void dft(double2* x) {
 // X[k] *= w1^k for k = 1..R-1 (outputs addressed through oidx)
 template <int R>
 __device__ __forceinline__ void twiddle(double2* x, double2 w1) {
+#ifdef TFFT_EXP_NO_FP64
+    x[0].x += w1.x;  // keep the table load alive
+    return;
+#endif
     double2 w = w1;
 #pragma unroll
     for (int k = 1; k < R; k++) {
@@ -132,12 +139,33 @@ __device__ __forceinline__ void unit_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Ping-pong between the two units of a CTA.  A unit alternates FP64-bound phases (butterflies) and LSU-bound phases
+// (exchanges, global stores); two free-running units share both pipes evenly, which keeps them in step and
+// leaves each pipe idle while the other is busy (measured: the second unit added only 15 %).  With the token
+// the LSU-bound phases strictly alternate between the units, so one unit's butterflies run under the other's
+// exchange.  acquire = bar.sync on my token (my 256 threads + 256 arrivals of the other unit), release = bar.arrive
+// on the other unit's token.  Unit 0 goes first (unit 1 pre-arrives once); `on` is switched off for the items
+// the other unit does not have, and unit 1 skips its very last release, so every barrier phase is complete.
+struct PingPong {
+    int me, other;
+    bool on;
+    __device__ __forceinline__ void acquire() const {
+        if (on) asm volatile("bar.sync %0, 512;\n" ::"r"(me) : "memory");
+    }
+    __device__ __forceinline__ void release() const {
+        if (on) asm volatile("bar.arrive %0, 512;\n" ::"r"(other) : "memory");
+    }
+};
+
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives ------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
     asm volatile(
@@ -201,10 +229,13 @@ __device__ __forceinline__ int xpos(int k1, int k2, int low) {
 template <int LOG2N>
 constexpr int xpad() { return LOG2N == 12 ? 16 : 0; }  // extra entries of a padded exchange buffer
 
-__device__ __forceinline__ unsigned lds_u8(unsigned saddr) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(saddr));
-    return v;
+// exact u8 -> double without a conversion instruction: 2^52 + v has v in its low mantissa word
+__device__ __forceinline__ double u8_to_double(unsigned v) {
+#ifdef TFFT_U8_I2F
+    return (double)v;
+#else
+    return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+#endif
 }
 
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
@@ -300,7 +331,7 @@ __device__ __forceinline__ void stage23(double* X, int tt, int c, double2 w1, do
 // Variant for passes whose L buffer is not a landing buffer (u8 forward rows): exchange 2 runs in
 // place in L with 16 B entries and the same XOR swizzle -> one barrier instead of three.
 template <int S, int LOG2N, bool PADDED = false>
-__device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, double2* x, int bar_id) {
+__device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, double2* x, int bar_id, const PingPong pp = PingPong{0, 0, false}) {
     using G = Geo<LOG2N, 1>;
     const int k1 = tt >> 4, m = tt & 15;
     dft<S, 16>(x);
@@ -308,6 +339,7 @@ __device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, 
     const int k1r = tt & (G::R1 - 1), k2r = tt / G::R1;
     [[maybe_unused]] double2* Lw = L + xpos<G::R1>(k1, 0, m);   // R1 == 16: the 16 accesses are Lw[16 k2] / Lr[n] (immediate offsets)
     [[maybe_unused]] const double2* Lr = L + xpos<G::R1>(k1r, k2r, 0);
+    pp.acquire();
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) {
         if constexpr (PADDED && G::R1 == 16) Lw[k2 << 4] = x[oidx<16>(k2)];
@@ -319,6 +351,7 @@ __device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, 
         if constexpr (PADDED && G::R1 == 16) x[n] = Lr[n];
         else x[n] = L[(PADDED ? xpos<G::R1>(k1r, k2r, n) : swz<G::R1>(k1r, k2r, n))];
     }
+    pp.release();
     dft<S, 16>(x);
 }
 
@@ -512,8 +545,17 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     constexpr int LOG2N = 12, VEC = 2;
     using G = Geo<LOG2N, VEC>;
     constexpr int BOX_ROWS = 256, NBOX = G::N / BOX_ROWS;
+    static_assert(NZ >= 1 && NZ <= NBOX && K3N >= 1 && K3N <= 16, "block counts");
+    // Only the exchange between stage 1 and stage 2 is a block-wide barrier.  Everything else is a hand-off to ONE
+    // thread that talks to the TMA engine, so the other 511 only arrive (non-blocking) on an mbarrier and move on:
+    //   lfree   (512 arrivals)  every thread has its stage-2 inputs      -> TL issues the next pair's box loads
+    //   xfree_a (1)             the previous pair's last store left X    -> everybody may write exchange 2
+    //   staged0 / staged1 (512) half h of the results is staged          -> TS0 / TS1 issue the box store
+    //   xfree_b (1)             the first half has been read out         -> everybody may stage the second half
+    // The three duties sit in three different warps, so no single warp carries all the waiting.
+    constexpr int TL = 0, TS0 = 160, TS1 = 320;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t full_bar;
+    __shared__ uint64_t full_bar, lfree, xfree_a, xfree_b, staged0, staged1;
     double2* L = (double2*)smem_raw;
     double* X = (double*)(smem_raw + G::L_BYTES);
     const int tid = threadIdx.x, c = tid & 1, tt = tid >> 1;
@@ -526,11 +568,15 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
 
     if (tid == 0) {
         mbar_init(&full_bar, 1);
+        mbar_init(&lfree, 512);
+        mbar_init(&xfree_a, 1);
+        mbar_init(&xfree_b, 1);
+        mbar_init(&staged0, 512);
+        mbar_init(&staged1, 512);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     __syncthreads();
 
-    static_assert(NZ >= 1 && NZ <= NBOX && K3N >= 1 && K3N <= 16, "block counts");
     auto issue_load = [&](long long it) {
         const int plane = (int)(it / a.groups_per_plane), g = (int)(it % a.groups_per_plane);
         mbar_expect_tx(&full_bar, (unsigned)((size_t)NZ * BOX_ROWS * VEC * 16));
@@ -540,18 +586,21 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
 
     const long long stride = gridDim.x;
     long long item = blockIdx.x;
-    if (tid == 0 && item < a.nitems) issue_load(item);
+    if (tid == TL && item < a.nitems) issue_load(item);
     unsigned parity = 0;
-    for (; item < a.nitems; item += stride) {
+    for (; item < a.nitems; item += stride, parity ^= 1) {
         mbar_wait(&full_bar, parity);
-        parity ^= 1;
         stage1<S, LOG2N, VEC, false, NZ>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
         __syncthreads();
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
-        if (tid == 0) tma_wait_read_all();  // the previous pair's last box store has finished reading X
-        __syncthreads();                    // L is free, X is free
-        if (tid == 0 && item + stride < a.nitems) {
+        mbar_arrive(&lfree);
+        if (tid == TS1) {  // its own store of the previous pair's second half has finished reading X
+            tma_wait_read_all();
+            mbar_arrive(&xfree_a);
+        }
+        if (tid == TL && item + stride < a.nitems) {
+            mbar_wait(&lfree, parity);  // L is free
             fence_async_proxy();
             issue_load(item + stride);
         }
@@ -559,6 +608,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         dft<S, 16>(x);
         twiddle<16>(x, ttw.s2v());
         double2 z[16];
+        mbar_wait(&xfree_a, parity);
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].x;
         __syncwarp();
@@ -572,28 +622,45 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
         dft<S, 16>(z);  // z[oidx(k3)] = output row k1 + 16*m + 256*k3 of column c
         const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
+        // ---- first half of the results: rows with k3 < 8
+        __syncwarp();  // every lane is past its reads of the slice
 #pragma unroll
-        for (int h = 0; h < (K3N > 8 ? 2 : 1); h++) {
-            if (h == 1) __syncthreads();  // the first half has been read out by the TMA engine
-            __syncwarp();                 // every lane is past its reads of the slice
+        for (int k3 = 0; k3 < 8; k3++) {
+            if (k3 >= K3N) continue;  // rows the store map clips anyway
+            double2 v = z[oidx<16>(k3)];
+            v.x *= scale; v.y *= scale;
+            Sw[(k3 * 16 + m) * VEC + c] = v;
+        }
+        fence_async_proxy();
+        mbar_arrive(&staged0);
+        if (tid == TS0) {
+            mbar_wait(&staged0, parity);
+            // smem image [k1][k3][k2][2 columns] -> rows k1 + 16 k2 + 256 k3 (map dims: col, k2, k3, k1, plane)
+            tma_store_5d(&out_map, X, g * VEC * 2, 0, 0, 0, plane);
+            tma_commit();
+            tma_wait_read_all();
+            mbar_arrive(&xfree_b);
+        }
+        // ---- second half: rows with 8 <= k3 < K3N
+        if constexpr (K3N > 8) {
+            mbar_wait(&xfree_b, parity);  // the first half has been read out by the TMA engine
 #pragma unroll
-            for (int k3 = 8 * h; k3 < 8 * h + 8; k3++) {
-                if (k3 >= K3N) continue;  // rows the store map clips anyway
+            for (int k3 = 8; k3 < 16; k3++) {
+                if (k3 >= K3N) continue;
                 double2 v = z[oidx<16>(k3)];
                 v.x *= scale; v.y *= scale;
-                Sw[((k3 - 8 * h) * 16 + m) * VEC + c] = v;
+                Sw[((k3 - 8) * 16 + m) * VEC + c] = v;
             }
             fence_async_proxy();
-            __syncthreads();
-            if (tid == 0) {
-                // smem image [k1][k3][k2][2 columns] -> rows k1 + 16 k2 + 256 k3 (map dims: col, k2, k3, k1, plane)
-                tma_store_5d(&out_map, X, g * VEC * 2, 0, 8 * h, 0, plane);
+            mbar_arrive(&staged1);
+            if (tid == TS1) {
+                mbar_wait(&staged1, parity);
+                tma_store_5d(&out_map, X, g * VEC * 2, 0, 8, 0, plane);
                 tma_commit();
-                if (h == 0) tma_wait_read_all();
             }
         }
     }
-    if (tid == 0) tma_wait_all();
+    if (tid == TS0 || tid == TS1) tma_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -774,6 +841,7 @@ struct R2CArgs {
     uint8_t* img_out;
     long long nitems;   // nimg * ceil(H/2) row pairs
     int W, H, PW, PH, ld, center;
+    int pingpong;       // experiment switch (TFFT_PINGPONG=1): LSU phases of the two units of a CTA strictly alternate
 };
 
 // ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
@@ -840,9 +908,19 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         while (clock64() - t0 < STAGGER_CYCLES) {}
     }
     unit_bar(bar_id, G::UT);
+    // ping-pong with the other unit (two-unit CTAs only): tokens are used for the items both units have
+    long long common = 0;
+    if (UNITS == 2 && a.pingpong) {
+        const long long first1 = (long long)blockIdx.x * UNITS + 1;
+        common = first1 < a.nitems ? (a.nitems - 1 - first1) / stride + 1 : 0;
+    }
+    PingPong pp{8 + unit, 8 + (unit ^ 1), common > 0};
+    if (unit == 1) pp.release();  // unit 0 goes first
+    long long jitem = 0;
     int buf = 0;
     if (item < a.nitems) issue_rows(item, 0);
-    for (; item < a.nitems; item += stride, buf ^= 1) {
+    for (; item < a.nitems; item += stride, buf ^= 1, jitem++) {
+        pp.on = jitem < common;
         cp_async_wait_all();
         unit_bar(bar_id, G::UT);
         if (item + stride < a.nitems) issue_rows(item + stride, buf ^ 1);
@@ -855,31 +933,36 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         const uint8_t* r1 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + row_bytes) & 15) + (size_t)tt * 3;
         for (int ch = 0; ch < 3; ch++) {
             // ---- stage 1 on z = row0 + i*row1 (plane split, centre sign, zero pad fused; S:383-398)
+            double2 x[16];
 #pragma unroll
             for (int j = 0; j < G::J1; j++) {
                 const int m = tt + j * G::TP;
-                double2 x[G::R1];
+                double2* xj = x + j * G::R1;
 #pragma unroll
                 for (int n = 0; n < G::R1; n++) {
                     const unsigned o = (unsigned)((n * 256 + j * G::TP) * 3) + (unsigned)ch;
-                    double v0 = (double)r0[o], v1 = (double)r1[o];
+                    double v0 = u8_to_double(r0[o]), v1 = u8_to_double(r1[o]);
                     if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); x parity == m parity
                         if ((m + y0) & 1) v0 = -v0; else v1 = -v1;
                     }
-                    x[n] = make_double2(v0, v1);
+                    xj[n] = make_double2(v0, v1);
                 }
-                dft<+1, G::R1>(x);
+                dft<+1, G::R1>(xj);
                 double2 w1 = a.tw[(size_t)m << (TW_LOG2 - LOG2N)];
-                twiddle<G::R1>(x, w1);
-#pragma unroll
-                for (int k = 0; k < G::R1; k++) L[k * 256 + m] = x[oidx<G::R1>(k)];
+                twiddle<G::R1>(xj, w1);
             }
+            pp.acquire();  // LSU phase 1: exchange 1
+#pragma unroll
+            for (int j = 0; j < G::J1; j++)
+#pragma unroll
+                for (int k = 0; k < G::R1; k++) L[k * 256 + tt + j * G::TP] = x[j * G::R1 + oidx<G::R1>(k)];
             unit_bar(bar_id, G::UT);
-            double2 x[16];
             stage2_load<LOG2N, 1>(L, tt, 0, x);
+            pp.release();
             unit_bar(bar_id, G::UT);
-            stage23_inplace<+1, LOG2N, true>(L, tt, ttw.s2v(), x, bar_id);  // x[oidx(k3)] = Z[tt + TP*k3]
-            unit_bar(bar_id, G::UT);                                        // all reads of L done
+            stage23_inplace<+1, LOG2N, true>(L, tt, ttw.s2v(), x, bar_id, pp);  // LSU phase 2 inside; x[oidx(k3)] = Z[tt + TP*k3]
+            if (pp.on) pp.acquire();          // LSU phase 3: split + stores (the token sync also orders the reads of L)
+            else unit_bar(bar_id, G::UT);     // all reads of L done
             // ---- split Z into the spectra of the two real rows: partners Z[N-k] through L
 #pragma unroll
             for (int k3 = 8; k3 < 16; k3++) L[tt + G::TP * (k3 - 8)] = x[oidx<16>(k3)];  // Z[N/2 + j] at L[j]
@@ -901,7 +984,11 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                 out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
                 if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
             }
-            unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
+            if (pp.on) {  // L is rewritten only after the next acquire, which syncs the unit
+                if (!(unit == 1 && ch == 2 && jitem == common - 1)) pp.release();  // unit 1 keeps its very last token
+            } else {
+                unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
+            }
         }
     }
 }
@@ -1233,6 +1320,8 @@ cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
     a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
     a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
     a.nitems = (long long)(p.nplanes / 3) * ((p.H + 1) / 2);
+    static const int pingpong = getenv("TFFT_PINGPONG") ? atoi(getenv("TFFT_PINGPONG")) : 0;
+    a.pingpong = pingpong;
     return p.center ? run_r2c_c<LOG2N, UNITS, INV, true>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false>(L, a);
 }
 

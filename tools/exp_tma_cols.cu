@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(128, 1) k(const __grid_constant__ CUtensorMap 
 }
 
 int main(int argc, char** argv) {
-    const int PH = 4096, PW = 4096, planes = 24;
+    // usage: exp_tma_cols [PW [planes [reps]]] -- a small PW*planes keeps the working set inside the 126 MB L2
+    const int PH = 4096, PW = argc > 1 ? atoi(argv[1]) : 4096, planes = argc > 2 ? atoi(argv[2]) : 24, reps = argc > 3 ? atoi(argv[3]) : 4;
     const size_t P = (size_t)PH * PW;
     double* din; double* dout;
     CK(cudaMalloc(&din, planes * P * 16)); CK(cudaMalloc(&dout, planes * P * 16));
@@ -112,7 +113,7 @@ int main(int argc, char** argv) {
         enc(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, dout, dims2, strides2, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, c.sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         float best = 1e9;
-        for (int rep = 0; rep < 4; rep++) {
+        for (int rep = 0; rep < reps; rep++) {
             cudaEventRecord(e0);
             if (c.nbuf == 1) { CK(cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k<1><<<sms, 128, smem>>>(mi, mo, groups_per_plane, nitems, c.inner_d, c.rows_per_buf, boxes, buf_bytes); }
             else if (c.nbuf == 2) { CK(cudaFuncSetAttribute(k<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); k<2><<<sms, 128, smem>>>(mi, mo, groups_per_plane, nitems, c.inner_d, c.rows_per_buf, boxes, buf_bytes); }
