@@ -218,17 +218,31 @@ PassArgs base_args(tfft_ctx* ctx, double2* spec, int nimg, const Geom& g, int ce
     return a;
 }
 
+// The two generic passes of the large-size path (a padded dimension of 8192 / 16384).  A four-step pass leaves its
+// result in the scratch batch; instead of copying it back the next pass simply runs on the other buffer, and one copy
+// happens at the end only when an odd number of four-step passes ran.
+int c2c_two_passes(tfft_ctx* ctx, const Launcher& L, PassArgs a, double2* spec, double2* tmp, int nimg, const Geom& g, bool rows_first) {
+    double2 *cur = spec, *other = tmp;
+    for (int k = 0; k < 2; k++) {
+        const int axis = (k == 0) == rows_first ? 0 : 1;
+        a.axis = axis; a.log2n = axis == 0 ? g.lw : g.lh;
+        a.spec = cur; a.tmp = other;
+        const bool four = a.log2n > 12;
+        a.leave_in_tmp = four ? 1 : 0;
+        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        if (four) std::swap(cur, other);
+    }
+    if (cur != spec) CK(cudaMemcpyAsync(spec, cur, (size_t)nimg * 3 * g.P * sizeof(double2), cudaMemcpyDeviceToDevice, L.stream));
+    return TFFT_OK;
+}
+
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
 int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     if (g.large) {  // unfused: u8 -> planes (zero pad materialised), then two generic c2c passes
         { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_u8_to_planes(L, d_img, spec, nimg, g.W, g.H, g.PW, g.PH, center)); }
-        a.tmp = tmp; a.inverse = 0;
-        a.axis = 0; a.log2n = g.lw;
-        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
-        a.axis = 1; a.log2n = g.lh;
-        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
-        return TFFT_OK;
+        a.inverse = 0;
+        return c2c_two_passes(ctx, L, a, spec, tmp, nimg, g, /*rows_first=*/true);
     }
     const double cols = (double)g.ld;  // columns the workspace keeps (PW, or PW/2+16 in half mode)
     a.img_in = d_img;
@@ -247,11 +261,8 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
 int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, uint8_t* d_img, int nimg, const Geom& g, int center) {
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     if (g.large) {
-        a.tmp = tmp; a.inverse = 1;
-        a.axis = 1; a.log2n = g.lh;
-        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
-        a.axis = 0; a.log2n = g.lw;
-        { ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.P); CK(launch_fft_pass(L, a)); }
+        a.inverse = 1;
+        { int rc2 = c2c_two_passes(ctx, L, a, spec, tmp, nimg, g, /*rows_first=*/false); if (rc2) return rc2; }
         { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_planes_to_u8(L, spec, d_img, nimg, g.W, g.H, g.PW, g.PH, center)); }
         return TFFT_OK;
     }

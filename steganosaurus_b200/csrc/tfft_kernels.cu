@@ -245,6 +245,7 @@ static cudaError_t launch_fourstep(const Launcher& L, const PassArgs& a) {
     if (R == 2) fourstep_combine<2><<<grid, 256, 0, L.stream>>>(a.spec, a.tmp, a.tw, a.axis, a.PH, a.PW, a.log2n, a.inverse, total);
     else        fourstep_combine<4><<<grid, 256, 0, L.stream>>>(a.spec, a.tmp, a.tw, a.axis, a.PH, a.PW, a.log2n, a.inverse, total);
     TFFT_LAUNCH_CHECK(L);
+    if (a.leave_in_tmp) return cudaSuccess;
     return cudaMemcpyAsync(a.spec, a.tmp, (size_t)a.nplanes * a.PH * a.PW * sizeof(double2), cudaMemcpyDeviceToDevice, L.stream);
 }
 

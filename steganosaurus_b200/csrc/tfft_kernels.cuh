@@ -40,6 +40,7 @@ struct PassArgs {
     // Scratch plane batch of the same size as spec: needed by passes longer than 4096 points
     // (four-step scheme: strided 4096-point sub-transforms in place, radix-2/4 combine through tmp).
     double2* tmp;
+    int leave_in_tmp;  // four-step passes only: skip the copy back, the result stays in tmp (the caller ping-pongs)
 };
 
 // How a plane's spectrum is stored.  full: [PH][PW], ld = PW.  half (real planes, Hermitian):
