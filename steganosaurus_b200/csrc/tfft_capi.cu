@@ -48,6 +48,7 @@ struct tfft_ctx {
     uint64_t launches = 0;
     int fft_impl = 1;
     bool use_half = true;   // real-input symmetry (half-spectrum workspace); TFFT_SPECTRUM=full disables
+    bool use_wide = true;   // 8192-pixel rows on the half-spectrum path; TFFT_WIDE=0 keeps them on the unfused four-step path
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
     SpecLayout res_lay{0, 0, 0, 0};
     // resident spectra for the two-phase extract
@@ -102,7 +103,8 @@ struct Geom {
     size_t P;          // PH*PW
     size_t img_bytes;  // H*W*3
     int half, ld;      // workspace layout (SpecLayout)
-    int large;         // a padded dimension exceeds 4096: unfused conversion + four-step passes, full spectrum
+    int large;         // full-spectrum path for a padded dimension above 4096: unfused conversion + four-step passes
+    int col4;          // half-spectrum workspace whose column passes are four-step (PH = 8192 / 16384): needs the scratch batch
     size_t E;          // stored elements per plane = PH*ld
     SpecLayout lay() const { return SpecLayout{PH, PW, ld, half}; }
 };
@@ -117,9 +119,13 @@ int make_geom(const tfft_ctx* ctx, int W, int H, Geom& g) {
     g.lw = ilog2(g.PW); g.lh = ilog2(g.PH);
     g.P = (size_t)g.PW * g.PH;
     g.img_bytes = (size_t)W * H * 3;
-    // half-spectrum workspace whenever both axes run on the pencil kernels (512..4096 points)
-    g.half = (ctx && ctx->use_half && ctx->fft_impl != 0 && g.lw >= 9 && g.lw <= 12 && g.lh >= 9 && g.lh <= 12) ? 1 : 0;
-    g.large = (ctx && ctx->fft_impl != 0 && (g.lw > 12 || g.lh > 12)) ? 1 : 0;
+    // half-spectrum workspace whenever both axes run on the pencil kernels (512..4096 points), and for 8192-pixel
+    // rows (packed into the 4096-point fused row kernels) with any supported height
+    const bool ok = ctx && ctx->use_half && ctx->fft_impl != 0;
+    g.half = (ok && g.lw >= 9 && g.lw <= 12 && g.lh >= 9 && g.lh <= 12) ? 1 : 0;
+    if (ok && ctx->use_wide && g.lw == 13 && g.lh >= 9 && g.lh <= 14) g.half = 1;
+    g.col4 = (g.half && g.lh > 12) ? 1 : 0;
+    g.large = (!g.half && ctx && ctx->fft_impl != 0 && (g.lw > 12 || g.lh > 12)) ? 1 : 0;
     g.ld = g.half ? g.PW / 2 + 16 : g.PW;
     g.E = (size_t)g.PH * g.ld;
     return TFFT_OK;
@@ -167,7 +173,7 @@ void prof_drain(tfft_ctx* c) {
 
 // images per chunk so that `nslots` spectrum workspaces fit the limit
 int chunk_for(const tfft_ctx* ctx, const Geom& g, int n, int nslots) {
-    const size_t per_img = 3 * g.E * sizeof(double2) * (g.large ? 2 : 1);
+    const size_t per_img = 3 * g.E * sizeof(double2) * ((g.large || g.col4) ? 2 : 1);
     size_t c = ctx->ws_limit / nslots / per_img;
     if (c < 1) c = 1;
     if (c > (size_t)MAX_CHUNK) c = MAX_CHUNK;
@@ -179,7 +185,7 @@ int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, 
     int rc;
     const int nplanes = chunk * 3;
     if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
-    if (g.large && (rc = ensure(ctx, S.spec2, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
+    if ((g.large || g.col4) && (rc = ensure(ctx, S.spec2, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
     if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, CAND_CAP)))) return rc;
     if ((rc = ensure(ctx, S.medians, sizeof(double) * nplanes))) return rc;
     if ((rc = ensure(ctx, S.usable, sizeof(uint64_t) * chunk))) return rc;
@@ -252,6 +258,15 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
     a.img_in = nullptr;
     a.axis = 1; a.log2n = g.lh;  // in_rows stays H: the row pass left rows >= H unwritten (they are zero)
     if (g.half) { a.PW = g.ld; a.half = 0; }  // the column pass just sees a plane of ld columns
+    if (g.col4) {  // four-step columns read every row: materialise the zero rows the row pass skipped
+        if (g.H < g.PH)
+            CK(cudaMemset2DAsync(spec + (size_t)g.H * g.ld, (size_t)g.PH * g.ld * sizeof(double2), 0,
+                                 (size_t)(g.PH - g.H) * g.ld * sizeof(double2), (size_t)nimg * 3, L.stream));
+        a.in_rows = g.PH; a.tmp = tmp;
+        ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.PH * cols);
+        CK(launch_fft_pass(L, a));
+        return TFFT_OK;
+    }
     { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * cols + (double)g.PH * cols)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
@@ -270,7 +285,15 @@ int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403): the column pass does not store them
     if (g.half) { a.PW = g.ld; a.half = 0; }
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.PH * cols + (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    if (g.col4) {
+        a.out_rows = g.PH; a.tmp = tmp;
+        ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.PH * cols);
+        CK(launch_fft_pass(L, a));
+    } else {
+        ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.PH * cols + (double)g.H * cols));
+        CK(launch_fft_pass(L, a));
+    }
+    a.tmp = nullptr;
     a.PW = g.PW; a.half = g.half;
     a.axis = 0; a.log2n = g.lw;
     a.img_out = d_img;
@@ -385,6 +408,7 @@ int tfft_create(int device, tfft_ctx** out) {
     if (const char* hs = getenv("TFFT_HOST_SLOTS")) { int v = atoi(hs); if (v >= 1 && v <= NSLOT) HOST_SLOTS = v; }
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
+    if (const char* wd = getenv("TFFT_WIDE")) ctx->use_wide = atoi(wd) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
@@ -652,7 +676,7 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
-    if ((size_t)n * 3 * g.E * sizeof(double2) * (g.large ? 2 : 1) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
+    if ((size_t)n * 3 * g.E * sizeof(double2) * ((g.large || g.col4) ? 2 : 1) > ctx->ws_limit || n > MAX_CHUNK) return TFFT_E_NOMEM;
     Slot& S = ctx->slot[0];
     if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));

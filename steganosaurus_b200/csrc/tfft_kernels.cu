@@ -573,7 +573,7 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
 }
 
 constexpr int SCAN_UNROLL = 8;
-constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_THREADS = 256;
 constexpr uint32_t SCAN_TILE = SCAN_THREADS * SCAN_UNROLL;
 constexpr uint32_t SCAN_SBUF = 3072;  // members staged per CTA before one global reservation (24 KB)
 
@@ -629,7 +629,7 @@ __device__ __noinline__ void scan_cap_rare(double2 z, double q, uint64_t i, cons
 // (weight 1) and the zero pad columns (weight 0) are corrected per row afterwards -- counts directly, members
 // through the excess list cand_b that the weighted select subtracts -- so the hot loop carries no column
 // arithmetic.
-__global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __restrict__ spec, SpecLayout lay, MedianWork w,
+__global__ void __launch_bounds__(SCAN_THREADS, 3) median_scan(const double2* __restrict__ spec, SpecLayout lay, MedianWork w,
                                                             const Bracket* __restrict__ br, ScanCap cap) {
     __shared__ uint64_t s_buf[SCAN_SBUF];
     __shared__ unsigned s_cnt, s_base;
@@ -647,19 +647,22 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __
     const int lane = threadIdx.x & 31;
     const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    // double-buffered: the next tile's loads are in flight while this tile is classified
+    auto load_tile = [&](uint64_t t, double2* z) {
         const uint64_t base = t * SCAN_TILE + threadIdx.x;
-        double2 z[SCAN_UNROLL];
-        if (base - threadIdx.x + SCAN_TILE <= E) {
+        if (t < ntiles && t * SCAN_TILE + SCAN_TILE <= E) {
 #pragma unroll
             for (int u = 0; u < SCAN_UNROLL; u++) z[u] = __ldcs(pl + base + (uint64_t)u * SCAN_THREADS);
         } else {
 #pragma unroll
             for (int u = 0; u < SCAN_UNROLL; u++) {
                 const uint64_t i = base + (uint64_t)u * SCAN_THREADS;
-                z[u] = i < E ? __ldcs(pl + i) : make_double2(qnan, 0.0);  // NaN: neither below, member nor tiny
+                z[u] = (t < ntiles && i < E) ? __ldcs(pl + i) : make_double2(qnan, 0.0);  // NaN: neither below, member nor tiny
             }
         }
+    };
+    auto classify = [&](uint64_t t, const double2* z) {
+        const uint64_t base = t * SCAN_TILE + threadIdx.x;
 #pragma unroll
         for (int u = 0; u < SCAN_UNROLL; u++) {
             const double q = fma(z[u].x, z[u].x, z[u].y * z[u].y);
@@ -669,6 +672,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __
             below += lowq ? 1u : 0u;
             if (__any_sync(0xffffffffu, member)) scan_stage(member, z[u], w, ip, s_buf, &s_cnt);
             if (tiny) scan_cap_rare(z[u], q, base + (uint64_t)u * SCAN_THREADS, lay, cap, qcap_lo, w, ip, capb);
+        }
+    };
+    {
+        double2 za[SCAN_UNROLL], zb[SCAN_UNROLL];
+        uint64_t t = blockIdx.x;
+        if (t < ntiles) load_tile(t, za);
+        while (t < ntiles) {
+            load_tile(t + gridDim.x, zb);       // out-of-range tiles load nothing
+            classify(t, za);
+            t += gridDim.x;
+            if (t >= ntiles) break;
+            load_tile(t + gridDim.x, za);
+            classify(t, zb);
+            t += gridDim.x;
         }
     }
     long long acc = (long long)below * (lay.half ? 2 : 1);
@@ -849,8 +866,10 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     cap.magmin2 = magmin * magmin; cap.rlo = rlo; cap.rhi = rhi;
     {
         const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
-        static const unsigned cap_ctas = getenv("TFFT_SCAN_CTAS") ? (unsigned)atoi(getenv("TFFT_SCAN_CTAS")) : 296u;  // experiment switch
-        const unsigned cc = cap_ctas ? cap_ctas : 296u;
+        // long-lived CTAs (3 per SM resident): about two waves over the whole plane batch
+        static const unsigned cap_env = getenv("TFFT_SCAN_CTAS") ? (unsigned)atoi(getenv("TFFT_SCAN_CTAS")) : 0u;  // experiment switch
+        unsigned cc = cap_env ? cap_env : (unsigned)(2 * 3 * L.sm_count / (nplanes > 0 ? nplanes : 1));
+        if (!cap_env) cc = cc < 8 ? 8 : (cc > (unsigned)L.sm_count ? (unsigned)L.sm_count : cc);
         const unsigned per_plane = (unsigned)(ntiles < cc ? ntiles : cc);
         median_scan<<<dim3(per_plane, (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>(spec, lay, w, br, cap);
         TFFT_LAUNCH_CHECK(L);

@@ -857,10 +857,15 @@ struct R2CGeo {
     static constexpr size_t FWD_UNIT = LF_BYTES + 2 * UB;
 };
 
-template <int LOG2N, int UNITS, bool CENTER>
+// WIDE (LOG2N = 12 only): ONE real row of 2N = 8192 pixels per item through the N-point complex transform of
+// z[n] = x[2n] + i*x[2n+1]:  with E/O the spectra of the even/odd samples (the same Hermitian split as the row-pair
+// case), X[k] = E[k] + W^k O[k] and X[N-k] = conj(E[k] - W^k O[k]), W = exp(+2 pi i / 2N), k = 0..N/2, X[N/2] = Z[N/2].
+// The half-spectrum row then has N+1 = 4097 columns (ld = N + 16).
+template <int LOG2N, int UNITS, bool CENTER, bool WIDE = false>
 __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c(R2CArgs a) {
     using G = Geo<LOG2N, 1>;
     using RG = R2CGeo<LOG2N>;
+    static_assert(!WIDE || LOG2N == 12, "the wide variant packs an 8192-pixel row into a 4096-point transform");
     constexpr int N = G::N, NH = N / 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
@@ -870,7 +875,8 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
     const int bar_id = 1 + unit;
     const long long stride = (long long)gridDim.x * UNITS;
     long long item = (long long)blockIdx.x * UNITS + unit;
-    const int HP = (a.H + 1) / 2;  // row pairs per image
+    const int HP = WIDE ? a.H : (a.H + 1) / 2;  // items (row pairs, or single wide rows) per image
+    const int YS = WIDE ? 1 : 2;                // image rows per item
     const size_t row_bytes = (size_t)a.W * 3;
     const int nch = (int)((row_bytes + 15) >> 4) + 1;   // chunks per row: covers every 16 B phase of the row start
     const uintptr_t img_base = (uintptr_t)a.img_in;
@@ -879,15 +885,15 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
 
     auto pair_start = [&](long long it) -> uintptr_t {
         const long long img = it / HP;
-        const int y0 = 2 * (int)(it % HP);
+        const int y0 = YS * (int)(it % HP);
         return img_base + ((size_t)img * a.H + y0) * row_bytes;
     };
-    auto pair_rows = [&](long long it) -> int { return (2 * (int)(it % HP) + 1 < a.H) ? 2 : 1; };
+    auto pair_rows = [&](long long it) -> int { return (!WIDE && 2 * (int)(it % HP) + 1 < a.H) ? 2 : 1; };
     auto issue_rows = [&](long long it, int buf) {
         const uintptr_t s0 = pair_start(it);
         const int nrows = pair_rows(it);
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
+        for (int r = 0; r < (WIDE ? 1 : 2); r++) {  // wide: one row of up to 2N pixels fills the whole buffer
             const uintptr_t start = s0 + (size_t)r * row_bytes;
             const unsigned char* a0 = (const unsigned char*)(start & ~(uintptr_t)15);
             const int span = r < nrows ? (int)(start & 15) + (int)row_bytes : 0;  // bytes from a0 to the row end; absent row: all zero-fill
@@ -925,12 +931,14 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         unit_bar(bar_id, G::UT);
         if (item + stride < a.nitems) issue_rows(item + stride, buf ^ 1);
         const long long img = item / HP;
-        const int y0 = 2 * (int)(item % HP);
+        const int y0 = YS * (int)(item % HP);
         const int nrows = pair_rows(item);
         const uintptr_t s0 = pair_start(item);
-        // shared-space byte addresses of pixel tt of row 0 / row 1 (channel 0)
-        const uint8_t* r0 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + (s0 & 15) + (size_t)tt * 3;
-        const uint8_t* r1 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + row_bytes) & 15) + (size_t)tt * 3;
+        // shared-space byte addresses of the two real inputs of z[tt] (channel 0): pixel tt of row 0 / row 1, or
+        // (wide) pixels 2 tt and 2 tt + 1 of the one row
+        const uint8_t* r0 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + (s0 & 15) + (size_t)tt * (WIDE ? 6 : 3);
+        const uint8_t* r1 = WIDE ? r0 + 3
+                                 : smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + row_bytes) & 15) + (size_t)tt * 3;
         for (int ch = 0; ch < 3; ch++) {
             // ---- stage 1 on z = row0 + i*row1 (plane split, centre sign, zero pad fused; S:383-398)
             double2 x[16];
@@ -940,10 +948,10 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                 double2* xj = x + j * G::R1;
 #pragma unroll
                 for (int n = 0; n < G::R1; n++) {
-                    const unsigned o = (unsigned)((n * 256 + j * G::TP) * 3) + (unsigned)ch;
+                    const unsigned o = (unsigned)((n * 256 + j * G::TP) * (WIDE ? 6 : 3)) + (unsigned)ch;
                     double v0 = u8_to_double(r0[o]), v1 = u8_to_double(r1[o]);
-                    if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); x parity == m parity
-                        if ((m + y0) & 1) v0 = -v0; else v1 = -v1;
+                    if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); pair: x parity == m parity; wide: x = 2n, 2n+1
+                        if (((WIDE ? 0 : m) + y0) & 1) v0 = -v0; else v1 = -v1;
                     }
                     xj[n] = make_double2(v0, v1);
                 }
@@ -971,18 +979,41 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
             double2* out0 = a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
             double2* out1 = out0 + a.ld;
             const double2* Lp = L + NH - tt;
+            if constexpr (WIDE) {
+                // W^k = W^tt * (W^TP)^k3 with W = exp(2 pi i / 2N): table entry 2 tt, then constant rotations by 2 pi k3 / 32
+                const double2 wb = a.tw[(size_t)tt << (TW_LOG2 - LOG2N - 1)];
+                double2* outm = out0 + N - tt;  // X[N - k]
 #pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) {
-                const int k = tt + G::TP * k3;
-                const double2 z = x[oidx<16>(k3)];
-                const double2 zn = Lp[-G::TP * k3];  // Z[N-k] = L[(N-k) - N/2]; k = 0 reads L[NH] = Z[0]
-                out0[k] = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));            // (Z[k] + conj Z[N-k]) / 2
-                if (nrows == 2) out1[k] = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));  // (Z[k] - conj Z[N-k]) / 2i
-            }
-            if (tt < 16) {  // Nyquist column (real) and the zero pad columns N/2+1 .. N/2+15
-                const double2 z8 = x[oidx<16>(8)];
-                out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
-                if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
+                for (int k3 = 0; k3 < 8; k3++) {
+                    constexpr double C32[8] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                               0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
+                    constexpr double S32[8] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913};
+                    const double2 z = x[oidx<16>(k3)];
+                    const double2 zn = Lp[-G::TP * k3];
+                    const double2 E = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));
+                    const double2 O = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));
+                    const double2 w = k3 == 0 ? wb : cmulc<+1>(wb, C32[k3], S32[k3]);
+                    const double2 t = cmul(w, O);
+                    out0[tt + G::TP * k3] = make_double2(E.x + t.x, E.y + t.y);       // X[k]
+                    outm[-G::TP * k3] = make_double2(E.x - t.x, t.y - E.y);           // X[N-k] = conj(E - t)
+                }
+                if (tt == 0) out0[NH] = x[oidx<16>(8)];                               // X[N/2] = Z[N/2]
+                if (tt >= 1 && tt < 16) out0[N + tt] = make_double2(0.0, 0.0);        // pad columns N+1 .. N+15
+            } else {
+#pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) {
+                    const int k = tt + G::TP * k3;
+                    const double2 z = x[oidx<16>(k3)];
+                    const double2 zn = Lp[-G::TP * k3];  // Z[N-k] = L[(N-k) - N/2]; k = 0 reads L[NH] = Z[0]
+                    out0[k] = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));            // (Z[k] + conj Z[N-k]) / 2
+                    if (nrows == 2) out1[k] = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));  // (Z[k] - conj Z[N-k]) / 2i
+                }
+                if (tt < 16) {  // Nyquist column (real) and the zero pad columns N/2+1 .. N/2+15
+                    const double2 z8 = x[oidx<16>(8)];
+                    out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
+                    if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
+                }
             }
             if (pp.on) {  // L is rewritten only after the next acquire, which syncs the unit
                 if (!(unit == 1 && ch == 2 && jitem == common - 1)) pp.release();  // unit 1 keeps its very last token
@@ -1047,10 +1078,14 @@ struct C2RGeo {
     static constexpr size_t UNIT = LB + ((XB + 15) & ~(size_t)15);
 };
 
-template <int LOG2N, int UNITS, bool CENTER>
+// WIDE (LOG2N = 12 only): ONE half-spectrum row X[0..N] of a 2N = 8192-pixel image row per item.  With
+// E = (X[k] + conj X[N-k])/2 and O = W^-k (X[k] - conj X[N-k])/2 (W = exp(+2 pi i / 2N)) the N-point inverse transform of
+// Z = E + iO returns the even samples in the real part and the odd samples in the imaginary part.
+template <int LOG2N, int UNITS, bool CENTER, bool WIDE = false>
 __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r(R2CArgs a) {
     using G = Geo<LOG2N, 1>;
     using CG = C2RGeo<LOG2N>;
+    static_assert(!WIDE || LOG2N == 12, "the wide variant unpacks a 4096-point transform into an 8192-pixel row");
     constexpr int N = G::N, NH = N / 2, HL = NH + 1;  // HL entries per half row
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
@@ -1060,25 +1095,30 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
     const int bar_id = 1 + unit;
     const long long stride = (long long)gridDim.x * UNITS;
     long long item = (long long)blockIdx.x * UNITS + unit;
-    const int HP = (a.H + 1) / 2;
+    const int HP = WIDE ? a.H : (a.H + 1) / 2;
+    const int YS = WIDE ? 1 : 2;
     const size_t row_bytes = (size_t)a.W * 3;
-    const double scale = 1.0 / (double)N;  // S:357
+    const double scale = (WIDE ? 0.5 : 1.0) / (double)N;  // S:357 (wide: the halves of E and O folded in)
     ThreadTw<-1, LOG2N, 1> ttw;
     ttw.load(a.tw, tt);
 
     auto src_rows = [&](long long it, int ch) -> const double2* {
         const long long img = it / HP;
-        const int y0 = 2 * (int)(it % HP);
+        const int y0 = YS * (int)(it % HP);
         return a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
     };
     auto issue_loads = [&](long long it, int ch) {
         const double2* A = src_rows(it, ch);
-        const bool two = 2 * (int)(it % HP) + 1 < a.H;  // odd-H tail: the second row is absent (zero)
-        for (int e = tt; e < 2 * HL; e += G::UT) {
-            const bool isB = e >= HL;
-            const double2* src = isB ? A + a.ld + (e - HL) : A + e;
-            const bool valid = !isB || two;
-            cp_async16(&L[e], valid ? (const void*)src : (const void*)a.spec, valid ? 16 : 0);
+        if constexpr (WIDE) {
+            for (int e = tt; e < N + 1; e += G::UT) cp_async16(&L[e], A + e, 16);
+        } else {
+            const bool two = 2 * (int)(it % HP) + 1 < a.H;  // odd-H tail: the second row is absent (zero)
+            for (int e = tt; e < 2 * HL; e += G::UT) {
+                const bool isB = e >= HL;
+                const double2* src = isB ? A + a.ld + (e - HL) : A + e;
+                const bool valid = !isB || two;
+                cp_async16(&L[e], valid ? (const void*)src : (const void*)a.spec, valid ? 16 : 0);
+            }
         }
         cp_async_commit();
     };
@@ -1090,9 +1130,9 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
     if (item < a.nitems) issue_loads(item, 0);
     for (; item < a.nitems; item += stride) {
         const long long img = item / HP;
-        const int y0 = 2 * (int)(item % HP);
-        const bool two = y0 + 1 < a.H;
-        uint8_t* o0 = a.img_out + ((size_t)img * a.H + y0) * row_bytes + (size_t)tt * 3;
+        const int y0 = YS * (int)(item % HP);
+        const bool two = !WIDE && y0 + 1 < a.H;
+        uint8_t* o0 = a.img_out + ((size_t)img * a.H + y0) * row_bytes + (size_t)tt * (WIDE ? 6 : 3);
         uint8_t* o1 = o0 + row_bytes;
         for (int ch = 0; ch < 3; ch++) {
             cp_async_wait_all();
@@ -1105,18 +1145,41 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
                 const int m = tt + j * G::TP;
                 const double2* Lf = L + m;        // form 1: A = Lf[256 n], B = Lf[HL + 256 n]
                 const double2* Lb = L + N - m;    // form 2: A = Lb[-256 n], B = Lb[HL - 256 n]
-                const double smid = (m == 0) ? 1.0 : -1.0;
+                [[maybe_unused]] const double smid = (m == 0) ? 1.0 : -1.0;
+                if constexpr (WIDE) {
+                    // cos / sin of 2 pi n / 32: W^-k = conj(W^m) * conj(W^(256 n))
+                    constexpr double C32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785,
+                                                0.0, -0.19509032201612826785, -0.38268343236508977173, -0.55557023301960222474,
+                                                -0.70710678118654752440, -0.83146961230254523708, -0.92387953251128675613, -0.98078528040323044913};
+                    constexpr double S32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                                                0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913,
+                                                1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                                0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
+                    double2 wb = a.tw[(size_t)m << (TW_LOG2 - LOG2N - 1)];
+                    wb.y = -wb.y;  // conj(W^m)
 #pragma unroll
-                for (int n = 0; n < G::R1; n++) {
-                    if (n < G::R1 / 2) {
-                        const double2 A = Lf[256 * n], B = Lf[HL + 256 * n];
-                        x[j * G::R1 + n] = make_double2(A.x - B.y, A.y + B.x);
-                    } else if (n > G::R1 / 2) {
-                        const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
-                        x[j * G::R1 + n] = make_double2(A.x + B.y, B.x - A.y);
-                    } else {  // k = N/2 + m: element N/2 - m of both halves; m = 0 is the Nyquist bin itself (first form)
-                        const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
-                        x[j * G::R1 + n] = make_double2(fma(-smid, B.y, A.x), fma(smid, A.y, B.x));
+                    for (int n = 0; n < G::R1; n++) {
+                        const double2 A = Lf[256 * n], B = Lb[-256 * n];                         // X[k], X[N-k]
+                        const double2 E = make_double2(A.x + B.x, A.y - B.y);                     // X[k] + conj X[N-k]
+                        const double2 D = make_double2(A.x - B.x, A.y + B.y);                     // X[k] - conj X[N-k]
+                        const double2 w = n == 0 ? wb : cmulc<-1>(wb, C32[n], S32[n]);
+                        const double2 O = cmul(w, D);
+                        x[j * G::R1 + n] = make_double2(E.x - O.y, E.y + O.x);                    // E + iO
+                    }
+                } else {
+#pragma unroll
+                    for (int n = 0; n < G::R1; n++) {
+                        if (n < G::R1 / 2) {
+                            const double2 A = Lf[256 * n], B = Lf[HL + 256 * n];
+                            x[j * G::R1 + n] = make_double2(A.x - B.y, A.y + B.x);
+                        } else if (n > G::R1 / 2) {
+                            const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
+                            x[j * G::R1 + n] = make_double2(A.x + B.y, B.x - A.y);
+                        } else {  // k = N/2 + m: element N/2 - m of both halves; m = 0 is the Nyquist bin itself (first form)
+                            const double2 A = Lb[-256 * n], B = Lb[HL - 256 * n];
+                            x[j * G::R1 + n] = make_double2(fma(-smid, B.y, A.x), fma(smid, A.y, B.x));
+                        }
                     }
                 }
             }
@@ -1142,8 +1205,14 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
 #pragma unroll
             for (int k3 = 0; k3 < 16; k3++) {
                 const int k = tt + G::TP * k3;
-                if (k < a.W) {
-                    double v0 = x[oidx<16>(k3)].x * scale, v1 = x[oidx<16>(k3)].y * scale;
+                double v0 = x[oidx<16>(k3)].x * scale, v1 = x[oidx<16>(k3)].y * scale;
+                if constexpr (WIDE) {  // Re -> pixel 2k, Im -> pixel 2k+1 of the one row
+                    if constexpr (CENTER) {
+                        if (y0 & 1) v0 = -v0; else v1 = -v1;
+                    }
+                    if (2 * k < a.W) o0[G::TP * k3 * 6 + ch] = clamp8_fast(v0);
+                    if (2 * k + 1 < a.W) o0[G::TP * k3 * 6 + 3 + ch] = clamp8_fast(v1);
+                } else if (k < a.W) {
                     if constexpr (CENTER) {
                         if ((k + y0) & 1) v0 = -v0; else v1 = -v1;
                     }
@@ -1296,17 +1365,17 @@ cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
     return cudaGetLastError();
 }
 
-template <int LOG2N, int UNITS, bool INV, bool CENTER>
+template <int LOG2N, int UNITS, bool INV, bool CENTER, bool WIDE>
 cudaError_t run_r2c_c(const Launcher& L, const pk::R2CArgs& a) {
     using G = pk::Geo<LOG2N, 1>;
     const size_t smem = (INV ? pk::C2RGeo<LOG2N>::UNIT : pk::R2CGeo<LOG2N>::FWD_UNIT) * UNITS;
     cudaError_t e;
     if constexpr (INV) {
-        auto kern = pk::pencil_u8_inv_c2r<LOG2N, UNITS, CENTER>;
+        auto kern = pk::pencil_u8_inv_c2r<LOG2N, UNITS, CENTER, WIDE>;
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     } else {
-        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS, CENTER>;
+        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS, CENTER, WIDE>;
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     }
@@ -1314,15 +1383,16 @@ cudaError_t run_r2c_c(const Launcher& L, const pk::R2CArgs& a) {
     return cudaGetLastError();
 }
 
-template <int LOG2N, int UNITS, bool INV>
+// WIDE: p.PW = 8192 runs on the 4096-point kernels (LOG2N = 12), one image row per item
+template <int LOG2N, int UNITS, bool INV, bool WIDE = false>
 cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
     pk::R2CArgs a;
     a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
     a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
-    a.nitems = (long long)(p.nplanes / 3) * ((p.H + 1) / 2);
+    a.nitems = (long long)(p.nplanes / 3) * (WIDE ? p.H : (p.H + 1) / 2);
     static const int pingpong = getenv("TFFT_PINGPONG") ? atoi(getenv("TFFT_PINGPONG")) : 0;
     a.pingpong = pingpong;
-    return p.center ? run_r2c_c<LOG2N, UNITS, INV, true>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false>(L, a);
+    return p.center ? run_r2c_c<LOG2N, UNITS, INV, true, WIDE>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false, WIDE>(L, a);
 }
 
 // per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB
@@ -1378,6 +1448,11 @@ cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* h
         case 11: return dispatch<11>(L, p);
         case 10: return dispatch<10>(L, p);
         case 9: return dispatch<9>(L, p);
+        case 13:  // 8192-pixel rows of a half-spectrum workspace: packed into the 4096-point fused u8 kernels
+            if (p.half && p.axis == 0 && p.img_in) return run_r2c<12, Cfg<12>::U8F_UNITS, false, true>(L, p);
+            if (p.half && p.axis == 0 && p.img_out) return run_r2c<12, Cfg<12>::U8I_UNITS, true, true>(L, p);
+            *handled = false;
+            return cudaSuccess;
         default: *handled = false; return cudaSuccess;
     }
 }

@@ -95,7 +95,9 @@ def test_golden_embed_extract(ctx, name):
     (2048, 1024, 50000, False, 0.5), (513, 1025, 9000, False, 0.5), (3000, 200, 4000, False, 0.5),
     (5000, 300, 6000, False, 0.5), (700, 9000, 6000, True, 0.5),
     # 4096-point fused u8 row kernels (R2C / C2R): ragged row bytes, odd H (half-empty last pair), centre on and off
-    (3001, 601, 7000, True, 0.5), (2500, 520, 7000, False, 0.5), (4096, 513, 7000, True, 0.5)])
+    (3001, 601, 7000, True, 0.5), (2500, 520, 7000, False, 0.5), (4096, 513, 7000, True, 0.5),
+    # 8192-pixel rows packed into the 4096-point kernels (half-spectrum workspace, ld = 4112)
+    (8192, 600, 9000, True, 0.5), (4097, 513, 5000, False, 0.5), (6001, 1030, 9000, False, 0.5)])
 def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
     o = oracle()
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
@@ -323,3 +325,29 @@ def test_uhd_matches_reference_failure_mode(ctx):
     stego, usable, _ = ctx.embed_batch(cover[None], bins, bits)
     _, raw = ctx.extract_bits(stego, bins, 1)
     assert (raw[0] != bits[0]).mean() > 0.05
+
+
+def test_wide_half_path_matches_unfused_path():
+    """PW = 8192 with PH = 8192: the half-spectrum path (packed row kernels + four-step columns) against the
+    full-spectrum unfused path of the same library (TFFT_WIDE=0), which the oracle tests pin at smaller heights."""
+    import os
+    W, H, nbits = 4500, 4200, 40000
+    cover = synth.gen_texture(W, H, 77)
+    bins = synth.random_bins(8192, 8192, nbits, 5)
+    bits = synth.random_bits(1, nbits, 6)
+    res = {}
+    for wide in ("1", "0"):
+        os.environ["TFFT_WIDE"] = wide
+        try:
+            with sb.Context(0) as c:
+                stego, usable, med = c.embed_batch(cover[None], bins, bits)
+                _, raw = c.extract_bits(stego, bins, 1)
+                res[wide] = (stego, usable, med, raw)
+        finally:
+            os.environ.pop("TFFT_WIDE", None)
+    a, b = res["1"], res["0"]
+    assert_pixels(a[0][0], b[0][0])
+    assert int(a[1][0]) == int(b[1][0])
+    assert np.allclose(a[2], b[2], rtol=1e-11)
+    assert np.array_equal(a[3], b[3])
+    assert (a[3][0] != bits[0]).mean() < 0.5
