@@ -53,6 +53,7 @@ struct tfft_ctx {
     SpecLayout res_lay{0, 0, 0, 0};
     // resident spectra for the two-phase extract
     int res_n = 0, res_PH = 0, res_PW = 0;
+    double2* res_spec = nullptr;  // buffer of slot 0 that holds them
     char cuda_err[256] = {0};
     // per-kernel-kind timing (tfft_profile_*)
     bool prof_on = false;
@@ -243,7 +244,11 @@ int c2c_two_passes(tfft_ctx* ctx, const Launcher& L, PassArgs a, double2* spec, 
 }
 
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
-int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center) {
+// `where` (optional) receives the buffer that holds the spectrum afterwards: spec, or tmp when the four-step column
+// pass of a tall half-spectrum workspace left its result in the scratch batch (no copy back)
+int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center,
+                   double2** where = nullptr) {
+    if (where) *where = spec;
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     if (g.large) {  // unfused: u8 -> planes (zero pad materialised), then two generic c2c passes
         { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.P)); CK(launch_u8_to_planes(L, d_img, spec, nimg, g.W, g.H, g.PW, g.PH, center)); }
@@ -263,8 +268,10 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
             CK(cudaMemset2DAsync(spec + (size_t)g.H * g.ld, (size_t)g.PH * g.ld * sizeof(double2), 0,
                                  (size_t)(g.PH - g.H) * g.ld * sizeof(double2), (size_t)nimg * 3, L.stream));
         a.in_rows = g.PH; a.tmp = tmp;
+        a.leave_in_tmp = where ? 1 : 0;
         ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.PH * cols);
         CK(launch_fft_pass(L, a));
+        if (where) *where = tmp;
         return TFFT_OK;
     }
     { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * cols + (double)g.PH * cols)); CK(launch_fft_pass(L, a)); }
@@ -285,10 +292,11 @@ int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
     a.axis = 1; a.log2n = g.lh; a.inverse = 1;
     a.out_rows = g.H;  // rows >= H are cropped away (S:399-403): the column pass does not store them
     if (g.half) { a.PW = g.ld; a.half = 0; }
-    if (g.col4) {
-        a.out_rows = g.PH; a.tmp = tmp;
+    if (g.col4) {  // four-step: the result lands in the other buffer, which the row pass then reads
+        a.out_rows = g.PH; a.tmp = tmp; a.leave_in_tmp = 1;
         ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.PH * cols);
         CK(launch_fft_pass(L, a));
+        a.spec = tmp; a.leave_in_tmp = 0;
     } else {
         ProfScope ps(ctx, L.stream, TFFT_K_COL_INV, (double)nimg * 3.0 * 16.0 * ((double)g.PH * cols + (double)g.H * cols));
         CK(launch_fft_pass(L, a));
@@ -305,9 +313,10 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
                 const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits, const double* d_jitter,
                 double alpha, int center, double magmin, double rmin, double rmax,
                 uint8_t* d_stego, uint64_t* d_usable, double* d_median) {
-    double2* spec = (double2*)S.spec.p;
-    int rc = forward_images(ctx, L, spec, (double2*)S.spec2.p, d_cover, nimg, g, center);
+    double2* spec = nullptr;  // whichever of the slot's two buffers holds the spectrum
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec);
     if (rc) return rc;
+    double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
     const int m = std::min(g.PH, g.PW);
@@ -315,15 +324,15 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
       CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
     { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
       CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
-    return inverse_images(ctx, L, spec, (double2*)S.spec2.p, d_stego, nimg, g, center);
+    return inverse_images(ctx, L, spec, other, d_stego, nimg, g, center);
 }
 
 // nhdr == 0: one segment of `rep`; nhdr > 0: rep-3 header segment + rep-7 payload segment (S:1223-1268)
 int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_stego, int nimg, const Geom& g,
                   const uint32_t* d_bins, size_t nbins, int rep, size_t nhdr, const double* d_jitter, double alpha, int center,
                   uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw) {
-    double2* spec = (double2*)S.spec.p;
-    int rc = forward_images(ctx, L, spec, (double2*)S.spec2.p, d_stego, nimg, g, center);
+    double2* spec = nullptr;
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec);
     if (rc) return rc;
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
@@ -681,7 +690,7 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
     Launcher L = make_launcher(ctx, S.stream);
-    if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center))) return rc;
+    if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center, &ctx->res_spec))) return rc;
     CK(cudaStreamSynchronize(S.stream));
     ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay();
     return TFFT_OK;
@@ -703,7 +712,7 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
     if ((rc = upload_bins(ctx, bins, nbins, jitter, S.stream))) return rc;
     Launcher L = make_launcher(ctx, S.stream);
     ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (16.0 + 4.0));
-    CK(launch_extract(L, (const double2*)S.spec.p, n, ctx->res_lay, (const uint32_t*)ctx->bins.p, nbins, rep,
+    CK(launch_extract(L, (const double2*)ctx->res_spec, n, ctx->res_lay, (const uint32_t*)ctx->bins.p, nbins, rep,
                       jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
                       out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr));
     if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes, S.outbytes.p, (size_t)n * nb, cudaMemcpyDeviceToHost, S.stream));
@@ -721,11 +730,11 @@ int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int c
     if (ctx->res_lay.half) {  // expand the half-spectrum workspace for the caller
         if ((rc = ensure(ctx, ctx->full, full_bytes))) return rc;
         Launcher L = make_launcher(ctx, S.stream);
-        CK(launch_expand_half(L, (const double2*)S.spec.p, (double2*)ctx->full.p, 3, ctx->res_lay));
+        CK(launch_expand_half(L, (const double2*)ctx->res_spec, (double2*)ctx->full.p, 3, ctx->res_lay));
         CK(cudaStreamSynchronize(S.stream));
         CK(cudaMemcpy(out_c64, ctx->full.p, full_bytes, cudaMemcpyDeviceToHost));
     } else {
-        CK(cudaMemcpy(out_c64, S.spec.p, full_bytes, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out_c64, ctx->res_spec, full_bytes, cudaMemcpyDeviceToHost));
     }
     return TFFT_OK;
 }
