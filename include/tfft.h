@@ -22,6 +22,12 @@
  * their work on that stream and return without synchronising.  The others take HOST
  * pointers (pinned memory from tfft_host_alloc recommended), copy in/out on internal
  * streams and are synchronous at return.
+ *
+ * Environment switches (read once; the defaults are the fast paths and none changes a result beyond
+ * rounding): TFFT_FFT_IMPL=v0|lsu (baseline shared-memory kernel / cp.async column kernel),
+ * TFFT_SPECTRUM=full (no Hermitian halving), TFFT_WIDE=0 (8192-pixel rows and tall images on the
+ * unfused four-step path), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
+ * images per chunk, chunks in flight), TFFT_PINGPONG=1, TFFT_ROW_UNITS=1, TFFT_SCAN_CTAS (experiments).
  */
 #ifndef TFFT_H
 #define TFFT_H

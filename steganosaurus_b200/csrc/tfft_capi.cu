@@ -67,7 +67,9 @@ struct tfft_ctx {
 
 namespace {
 
-constexpr uint32_t CAND_CAP = 1u << 19;  // median: sample (<= 2^18 keys) and bracket members per plane
+// median: sample (<= 2^18 keys) and bracket members per plane.  The bracket holds ~1.2 % of the stored elements, so
+// planes beyond 2^25 bins (8192 x 8192 and up) get a larger list instead of falling back to the generic passes.
+inline uint32_t cand_cap_for(size_t P) { return P > ((size_t)1 << 25) ? (1u << 21) : (1u << 19); }
 constexpr int MAX_CHUNK = 64;
 static int HOST_CHUNK = 8;  // host-buffer entry points: small chunks so H2D / kernels / D2H of neighbouring chunks overlap (TFFT_HOST_CHUNK)
 
@@ -125,6 +127,7 @@ int make_geom(const tfft_ctx* ctx, int W, int H, Geom& g) {
     const bool ok = ctx && ctx->use_half && ctx->fft_impl != 0;
     g.half = (ok && g.lw >= 9 && g.lw <= 12 && g.lh >= 9 && g.lh <= 12) ? 1 : 0;
     if (ok && ctx->use_wide && g.lw == 13 && g.lh >= 9 && g.lh <= 14) g.half = 1;
+    if (ok && ctx->use_wide && g.lw >= 9 && g.lw <= 12 && g.lh >= 13 && g.lh <= 14) g.half = 1;  // tall: four-step columns
     g.col4 = (g.half && g.lh > 12) ? 1 : 0;
     g.large = (!g.half && ctx && ctx->fft_impl != 0 && (g.lw > 12 || g.lh > 12)) ? 1 : 0;
     g.ld = g.half ? g.PW / 2 + 16 : g.PW;
@@ -187,7 +190,7 @@ int ensure_slot(tfft_ctx* ctx, Slot& S, const Geom& g, int chunk, bool need_io, 
     const int nplanes = chunk * 3;
     if ((rc = ensure(ctx, S.spec, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
     if ((g.large || g.col4) && (rc = ensure(ctx, S.spec2, (size_t)nplanes * g.E * sizeof(double2)))) return rc;
-    if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, CAND_CAP)))) return rc;
+    if ((rc = ensure(ctx, S.med, median_work_bytes(nplanes, cand_cap_for(g.P))))) return rc;
     if ((rc = ensure(ctx, S.medians, sizeof(double) * nplanes))) return rc;
     if ((rc = ensure(ctx, S.usable, sizeof(uint64_t) * chunk))) return rc;
     if (need_io) {
@@ -318,7 +321,7 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     if (rc) return rc;
     double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     MedianWork mw;
-    median_work_carve(mw, S.med.p, nimg * 3, CAND_CAP);
+    median_work_carve(mw, S.med.p, nimg * 3, cand_cap_for(g.P));
     const int m = std::min(g.PH, g.PW);
     { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.E);
       CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
@@ -826,9 +829,9 @@ int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec, int n, int PH,
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     Slot& S = ctx->slot[1];
-    if ((rc = ensure(ctx, S.med, median_work_bytes(n * 3, CAND_CAP)))) return rc;
+    if ((rc = ensure(ctx, S.med, median_work_bytes(n * 3, cand_cap_for((size_t)PH * PW))))) return rc;
     MedianWork mw;
-    median_work_carve(mw, S.med.p, n * 3, CAND_CAP);
+    median_work_carve(mw, S.med.p, n * 3, cand_cap_for((size_t)PH * PW));
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
     const int m = std::min(PH, PW);
     ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)n * 3.0 * 16.0 * (double)PH * PW);
