@@ -191,7 +191,9 @@ int png_save(const char* path, const uint8_t* rgb, int W, int H) {
     }
     // deflate in one stream (sizes may exceed uInt: loop)
     z_stream zs{};
-    if (deflateInit(&zs, 6) != Z_OK) return 0;
+    // TFFT_PNG_LEVEL (0..9, default 6): any valid lossless PNG is fine for the pipeline, level 1 is ~3x faster
+    static const int level = [] { const char* e = getenv("TFFT_PNG_LEVEL"); int v = e ? atoi(e) : 6; return v < 0 ? 0 : (v > 9 ? 9 : v); }();
+    if (deflateInit(&zs, level) != Z_OK) return 0;
     std::vector<uint8_t> comp;
     comp.resize(raw.size() / 2 + 4096);
     size_t in_pos = 0, out_pos = 0;

@@ -363,6 +363,17 @@ int upload_bins(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, const double*
 
 inline size_t dec_bytes(size_t nbins, int rep) { return (nbins / (size_t)rep + 7) / 8; }
 
+// Chunk sizes of the host pipeline: a short ramp (chunk/4, chunk/2) fills the H2D -> kernels -> D2H pipeline quickly
+// and a short last chunk drains it quickly; everything in between is `chunk` images.
+inline int next_chunk(int i0, int n, int chunk, int done_chunks) {
+    const int rem = n - i0, q = std::max(1, chunk / 4), h = std::max(1, chunk / 2);
+    if (n <= 2 * chunk) return std::min(chunk, rem);       // small batches: nothing to ramp
+    if (done_chunks == 0) return q;
+    if (done_chunks == 1) return h;
+    if (rem <= chunk + q) return rem > q ? rem - q : rem;   // tail: (rem - q) then q
+    return chunk;
+}
+
 // host-side sanity of a bin list: plane in 0..2 and linear index inside the padded plane
 bool bins_ok(const uint32_t* bins, size_t n, size_t P) {
     for (size_t i = 0; i < n; i++)
@@ -545,10 +556,10 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
         return TFFT_OK;
     };
     int ci = 0;
-    for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
+    for (int i0 = 0, m = 0; i0 < n; i0 += m, ci++) {
         const int sl = ci % nslots;
         Slot& S = ctx->slot[sl];
-        const int m = std::min(chunk, n - i0);
+        m = next_chunk(i0, n, chunk, ci);
         cudaStream_t st = S.stream;
         if ((rc = drain(sl))) return rc;  // the slot's buffers are about to be reused
         CK(cudaMemcpyAsync(S.in.p, cover + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
@@ -630,10 +641,10 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
         return TFFT_OK;
     };
     int ci = 0;
-    for (int i0 = 0; i0 < n; i0 += chunk, ci++) {
+    for (int i0 = 0, m = 0; i0 < n; i0 += m, ci++) {
         const int sl = ci % nslots;
         Slot& S = ctx->slot[sl];
-        const int m = std::min(chunk, n - i0);
+        m = next_chunk(i0, n, chunk, ci);
         cudaStream_t st = S.stream;
         if ((rc = drain(sl))) return rc;
         CK(cudaMemcpyAsync(S.in.p, stego + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));

@@ -1,0 +1,219 @@
+"""Image I/O pipeline around the batched CUDA hot path.
+
+The reference processes one PNG per process and spends far longer in the PNG codec and the KDF than the
+spectral work takes on a B200 (stb PNG encode alone is seconds per 4096^2 image).  Here the sequential host
+stages -- PNG decode (do_embed S:909), PBKDF2 + framing (S:927-995), PNG encode (S:1104), header parse and AEAD
+open (S:1223-1308) -- run on a pool of host threads (every one of them is a call into libtfft_host.so, which
+releases the GIL), while the images of one shape travel through `Context.embed_batch` / `forward_batch` +
+`read_bits` in chunks.  The on-image format, the pixels and the messages are exactly those of the single-image
+path (`host.embed_image` / `host.extract_image`); only the scheduling differs.
+
+Batching rules (the C ABI takes one bin list and one bit count per call): covers are grouped by
+(W, H, frame length); stego images by (W, H) -- their payload lengths may differ, the longest frame of the chunk
+is read for all of them and each image keeps its own prefix (the walk is a prefix-stable sequence, S:797-799).
+"""
+from __future__ import annotations
+
+import os
+from collections import defaultdict
+from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import host
+from .api import CapacityError, next_pow2
+
+
+@dataclass
+class Result:
+    """Outcome for one file: `error` carries the reference's message when the file failed."""
+    path: str
+    ok: bool = False
+    nbits: int = 0
+    plaintext: Optional[bytes] = None
+    error: Optional[str] = None
+
+
+@dataclass
+class Params:
+    alpha: float = 0.5
+    density: float = 0.7
+    rmin: float = 0.05
+    rmax: float = 0.45
+    magmin: float = 0.01
+    center: bool = False
+    pbkdf2_iter: int = 600000
+    jitter: float = 0.0
+
+
+def _default_workers() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def plan_embed_groups(shapes: Sequence[Tuple[int, int]], secret_lens: Sequence[int], chunk: int) -> List[List[int]]:
+    """Indices grouped by (W, H, frame length) and cut into chunks of at most `chunk` images (input order kept)."""
+    groups: Dict[Tuple[int, int, int], List[int]] = defaultdict(list)
+    for i, ((h, w), n) in enumerate(zip(shapes, secret_lens)):
+        groups[(w, h, 912 + 56 * (n + 16))].append(i)
+    out = []
+    for key in sorted(groups, key=lambda k: groups[k][0]):
+        idx = groups[key]
+        out.extend(idx[i:i + chunk] for i in range(0, len(idx), chunk))
+    return out
+
+
+def plan_extract_groups(shapes: Sequence[Tuple[int, int]], chunk: int) -> List[List[int]]:
+    groups: Dict[Tuple[int, int], List[int]] = defaultdict(list)
+    for i, (h, w) in enumerate(shapes):
+        groups[(w, h)].append(i)
+    out = []
+    for key in sorted(groups, key=lambda k: groups[k][0]):
+        idx = groups[key]
+        out.extend(idx[i:i + chunk] for i in range(0, len(idx), chunk))
+    return out
+
+
+class ImagePipeline:
+    """Thread-pooled PNG / KDF stages around one `steganosaurus_b200.Context`."""
+
+    def __init__(self, ctx, workers: Optional[int] = None, chunk: int = 16):
+        self.ctx = ctx
+        self.chunk = max(1, min(int(chunk), 64))
+        self.pool = ThreadPoolExecutor(max_workers=workers or _default_workers())
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- embed -------------------------------------------------------------------------------------------
+    def embed_files(self, covers: Sequence[str], outs: Sequence[str], secrets: Sequence[bytes], pw: bytes,
+                    params: Params = Params(), salts: Optional[Sequence[bytes]] = None) -> List[Result]:
+        assert len(covers) == len(outs) == len(secrets)
+        P = params
+        res = [Result(path=o) for o in outs]
+        imgs: List[Optional[np.ndarray]] = list(self.pool.map(_load_or_none, covers))
+        for r, im, c in zip(res, imgs, covers):
+            if im is None:
+                r.error = f"Failed to load {c}"
+        live = [i for i, im in enumerate(imgs) if im is not None]
+        salts_ = [os.urandom(16) if salts is None else salts[i] for i in range(len(covers))]
+        # KDF + AEAD + Rep-3/Rep-7 framing per image on the pool (600 000 PBKDF2 iterations each by default)
+        frames = dict(zip(live, self.pool.map(lambda i: host.frame_bits(pw, salts_[i], P.pbkdf2_iter, secrets[i])[0], live)))
+        plan = plan_embed_groups([imgs[i].shape[:2] for i in live], [len(secrets[i]) for i in live], self.chunk)
+        saves = []
+        for grp in plan:
+            idx = [live[k] for k in grp]
+            H, W, _ = imgs[idx[0]].shape
+            nbits = frames[idx[0]].size
+            try:
+                bins = host.cached_walk(pw, next_pow2(H), next_pow2(W), nbits, P.rmin, P.rmax, P.density)
+            except host.WalkExhausted:
+                # more bits than the annulus has bins: the reference stops at its capacity check (S:1009-1012),
+                # so report the same message with the capacity of each cover
+                cov = np.stack([imgs[i] for i in idx])
+                _, usable, _ = self.ctx.embed_batch(cov, np.zeros(0, np.uint32), np.zeros((len(idx), 0), np.uint8),
+                                                    P.alpha, P.center, P.magmin, P.rmin, P.rmax)
+                for k, i in enumerate(idx):
+                    res[i].error = f"Message too large. Need {nbits} bits (after ECC), capacity ~{int(usable[k])} bits."
+                continue
+            jit = host.jitter_values(pw, bins, P.jitter) if P.jitter else None
+            cov = np.stack([imgs[i] for i in idx])
+            bits = np.stack([frames[i] for i in idx])
+            try:
+                stego, usable, _ = self.ctx.embed_batch(cov, bins, bits, P.alpha, P.center, P.magmin, P.rmin, P.rmax, jitter=jit)
+                over = np.zeros(len(idx), bool)
+            except CapacityError as e:  # S:1009-1012: the offending images fail, the others are fine
+                stego, usable = e.stego, e.usable
+                over = np.asarray(usable) < nbits
+            for k, i in enumerate(idx):
+                if over[k]:
+                    res[i].error = f"Message too large. Need {nbits} bits (after ECC), capacity ~{int(usable[k])} bits."
+                else:
+                    res[i].nbits = nbits
+                    saves.append((i, self.pool.submit(host.png_save, outs[i], stego[k])))
+        for i, fut in saves:
+            try:
+                fut.result()
+                res[i].ok = True
+            except Exception as e:  # noqa: BLE001
+                res[i].error = str(e)
+        return res
+
+    # ---- extract -----------------------------------------------------------------------------------------
+    def extract_files(self, stegos: Sequence[str], pw: bytes, params: Params = Params()) -> List[Result]:
+        P = params
+        res = [Result(path=s) for s in stegos]
+        imgs = list(self.pool.map(_load_or_none, stegos))
+        for r, im, s in zip(res, imgs, stegos):
+            if im is None:
+                r.error = f"Failed to load {s}"
+        live = [i for i, im in enumerate(imgs) if im is not None]
+        opens = []
+        for grp in plan_extract_groups([imgs[i].shape[:2] for i in live], self.chunk):
+            idx = [live[k] for k in grp]
+            H, W, _ = imgs[idx[0]].shape
+            PH, PW = next_pow2(H), next_pow2(W)
+            self.ctx.forward_batch(np.stack([imgs[i] for i in idx]), P.center)   # one forward FFT per image, kept resident
+            hb = host.cached_walk(pw, PH, PW, 912, P.rmin, P.rmax, P.density)
+            hj = host.jitter_values(pw, hb, P.jitter) if P.jitter else None
+            hdrs, _ = self.ctx.read_bits(hb, 3, P.alpha, jitter=hj, want_raw=False)
+            clens = {}
+            for k, i in enumerate(idx):
+                hdr = hdrs[k].tobytes()
+                rc, clen, _, _ = host.parse_header(hdr)
+                if rc == 1:
+                    res[i].error = "Magic not found."
+                elif rc == 2:
+                    res[i].error = f"Unsupported version ({hdr[4]})."
+                elif 912 + 56 * (clen + 16) > 3 * PH * PW // 2:
+                    # a corrupted header: more frame bits than Hermitian-distinct bins exist.  The reference would walk
+                    # forever here; the bounded walk would take minutes to find out.
+                    res[i].error = "Payload truncated after ECC decode."
+                else:
+                    clens[k] = clen
+            # the longest frame that still fits the walk serves every image of the chunk
+            want = sorted(set(clens.values()), reverse=True)
+            allb = None
+            for clen in want:
+                try:
+                    allb = host.cached_walk(pw, PH, PW, 912 + 56 * (clen + 16), P.rmin, P.rmax, P.density)
+                    cmax = clen
+                    break
+                except host.WalkExhausted:
+                    for k, c in clens.items():
+                        if c == clen:
+                            res[idx[k]].error = "Payload truncated after ECC decode."
+            if allb is None:
+                continue
+            aj = host.jitter_values(pw, allb, P.jitter) if P.jitter else None
+            pays, _ = self.ctx.read_bits(allb[912:], 7, P.alpha, jitter=None if aj is None else aj[912:], want_raw=False)
+            for k, clen in clens.items():
+                if clen > cmax:
+                    continue
+                i = idx[k]
+                opens.append((i, self.pool.submit(host.open_payload, pw, P.pbkdf2_iter, hdrs[k].tobytes(),
+                                                  pays[k][:clen + 16].tobytes(), clen)))
+        for i, fut in opens:
+            ok, pt = fut.result()
+            if ok:
+                res[i].ok, res[i].plaintext = True, pt
+            else:
+                res[i].error = "Auth failed (wrong pass or data corrupted)."
+        return res
+
+
+def _load_or_none(path: str):
+    try:
+        return host.png_load(path)
+    except IOError:
+        return None

@@ -1,0 +1,71 @@
+"""Image I/O pipeline (steganosaurus_b200/pipeline.py): grouping logic and the thread-pooled
+PNG stages on CPU (stub context), the whole embed -> extract pipeline on the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from steganosaurus_b200 import host, pipeline, synth
+
+PASS = b"correct horse battery staple"
+
+
+def test_plan_groups_keep_order_and_split_by_shape_and_frame_length():
+    shapes = [(64, 64), (64, 64), (32, 48), (64, 64), (32, 48), (64, 64)]
+    lens = [5, 5, 5, 9, 5, 5]
+    plan = pipeline.plan_embed_groups(shapes, lens, chunk=2)
+    assert plan == [[0, 1], [5], [2, 4], [3]]
+    assert sorted(i for g in plan for i in g) == list(range(6))
+    assert pipeline.plan_extract_groups(shapes, chunk=3) == [[0, 1, 3], [5], [2, 4]]
+
+
+class _StubCtx:
+    """Stands in for the CUDA context: 'embeds' nothing, so the outputs must equal the covers."""
+
+    def embed_batch(self, cover, bins, bits, *a, **k):
+        assert bits.shape == (cover.shape[0], bins.size)
+        return cover.copy(), np.full(cover.shape[0], 10**9, np.uint64), np.zeros((cover.shape[0], 3))
+
+
+def test_embed_files_png_pool_roundtrip_with_stub_context(tmp_path):
+    covers, outs, secrets = [], [], []
+    for i, (w, h) in enumerate([(256, 192), (256, 192), (200, 260)]):
+        p = str(tmp_path / f"c{i}.png")
+        host.png_save(p, synth.gen_texture(w, h, i))
+        covers.append(p); outs.append(str(tmp_path / f"o{i}.png")); secrets.append(b"x" * (3 + i))
+    covers.append(str(tmp_path / "missing.png")); outs.append(str(tmp_path / "o3.png")); secrets.append(b"zz")
+    with pipeline.ImagePipeline(_StubCtx(), workers=3, chunk=2) as pl:
+        res = pl.embed_files(covers, outs, secrets, PASS, pipeline.Params(pbkdf2_iter=10))
+    assert [r.ok for r in res] == [True, True, True, False]
+    assert res[3].error.startswith("Failed to load")
+    assert [r.nbits for r in res[:3]] == [912 + 56 * (3 + i + 16) for i in range(3)]
+    for c, o in zip(covers[:3], outs[:3]):
+        assert np.array_equal(host.png_load(c), host.png_load(o))
+
+
+@pytest.mark.gpu
+def test_pipeline_embed_extract_on_gpu(tmp_path):
+    import steganosaurus_b200 as sb
+    from oracle import pyoracle as O
+    spec = [(256, 256, b"the eagle has landed"), (256, 256, b"second message, same length"[:20]), (256, 256, b"a longer secret " * 4),
+            (300, 200, b"ragged one"), (300, 200, b"ragged two"), (64, 64, b"far too long for this cover " * 40)]
+    covers, outs, secrets = [], [], []
+    for i, (w, h, s) in enumerate(spec):
+        p = str(tmp_path / f"c{i}.png")
+        host.png_save(p, synth.gen_cover(w, h, 20 + i))
+        covers.append(p); outs.append(str(tmp_path / f"s{i}.png")); secrets.append(s)
+    prm = pipeline.Params(pbkdf2_iter=1000)
+    with sb.Context(0) as ctx, pipeline.ImagePipeline(ctx, workers=4, chunk=2) as pl:
+        emb = pl.embed_files(covers, outs, secrets, PASS, prm)
+        assert [r.ok for r in emb] == [True] * 5 + [False]
+        assert emb[5].error.startswith("Message too large. Need ")
+        ext = pl.extract_files(outs[:5] + [covers[0]], PASS, prm)
+        assert [r.plaintext for r in ext[:5]] == secrets[:5]
+        assert not ext[5].ok and ext[5].error == "Magic not found."   # a clean cover carries nothing
+        # the single-image path reads the pipeline's output, and the reference CLI does too
+        assert host.extract_image(ctx, host.png_load(outs[2]), PASS, pbkdf2_iter=1000) == secrets[2]
+    if os.path.exists(O.REF_CLI):
+        p = subprocess.run([O.REF_CLI, "extract", "--in", outs[0], "--pass", PASS.decode(), "--pbkdf2_iter", "1000"],
+                           capture_output=True, text=True, timeout=120)
+        assert p.returncode == 0 and secrets[0].decode() in p.stdout, (p.stdout, p.stderr)
