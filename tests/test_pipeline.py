@@ -49,7 +49,7 @@ def test_pipeline_embed_extract_on_gpu(tmp_path):
     import steganosaurus_b200 as sb
     from oracle import pyoracle as O
     spec = [(256, 256, b"the eagle has landed"), (256, 256, b"second message, same length"[:20]), (256, 256, b"a longer secret " * 4),
-            (300, 200, b"ragged one"), (300, 200, b"ragged two"), (64, 64, b"far too long for this cover " * 40)]
+            (512, 256, b"second shape"), (512, 256, b"same shape, other length"), (64, 64, b"far too long for this cover " * 40)]
     covers, outs, secrets = [], [], []
     for i, (w, h, s) in enumerate(spec):
         p = str(tmp_path / f"c{i}.png")
