@@ -1,25 +1,27 @@
-// tfft_pencil.cu -- the fast FFT passes ("pencil" kernels) for N = 512 .. 4096.
+// tfft_pencil.cu -- the fast FFT passes ("pencil" kernels) for N = 512 .. 4096 (and 8192-pixel rows).
 //
 // A pencil is one row or one column of a padded plane.  N = R1 * 16 * 16 with R1 = N/256 in
 // {2,4,8,16}: three Cooley-Tukey stages (decimation in frequency) whose butterflies live in
 // registers (16 complex doubles per thread); data moves between stages through shared memory:
 //
-//   global --cp.async 16B--> L (dense landing buffer, 16 B entries)
-//   stage 1 (radix R1, stride 256)  in place in L                       [1 barrier]
-//   stage 2 (radix 16, stride 16)   reads L, then L is free: the NEXT pencil's cp.async loads
-//                                   are issued here and overlap everything below
-//   exchange 2 through X (8 B entries, re then im, XOR-swizzled -> conflict-free)  [3 barriers]
-//   stage 3 (radix 16, stride 1)    results leave the registers straight to global memory
+//   landing buffer L (rows: cp.async 16 B; columns: TMA box loads), dense 16 B entries
+//   stage 1 (radix R1, stride 256)  in place in L                                   [1 barrier]
+//   stage 2 (radix 16, stride 16)   reads L, then L is free: the NEXT pencil's loads are issued here
+//   exchange 2                      rows: padded / XOR-swizzled buffer; 4096-point columns: a warp-private
+//                                   4 KB transpose (after stage 1 the sixteen 256-point problems are independent)
+//   stage 3 (radix 16, stride 1)    results go to the epilogue: Hermitian split + STG (forward rows), u8 quantiser
+//                                   (inverse rows), staging + TMA box stores (columns)
 //
-// A "unit" is the set of threads that owns one L/X pair and works through its own stream of
-// pencils (persistent, static round-robin); a CTA hosts several units that only synchronise
-// among themselves (named barriers), so one unit's shared-memory phase overlaps another's FP64
-// phase.  Column passes process VEC adjacent columns per unit with the column index on the
-// fastest lanes, so every global access is a full 32 B sector (VEC=2) or more.
+// Kernels:
+//   pencil_u8_fwd_r2c / pencil_u8_inv_c2r   fused u8 RGB <-> half-spectrum rows; two image rows share one complex
+//                                           transform, or (WIDE) one 8192-pixel row is packed into one
+//   pencil_col_tma_w                        4096-point column pairs on the TMA engine, mbarrier hand-offs, zero-block skipping
+//   pencil_col_tma, pencil_c2c, pencil_u8_fwd/inv   other sizes / full-spectrum variants / LSU fallback
 //
-// Fused variants: u8 RGB row -> three forward row pencils (plane split, centre sign, zero pad;
-// to_planes_u8 S:383, apply_center S:392, pad_to_fft S:393) and three inverse row pencils -> u8 RGB
-// row (scale, crop, centre, round, clamp, interleave; S:357, ifft_crop S:399, from_planes_u8 S:387).
+// A "unit" is the set of threads that owns one buffer set and works through its own stream of pencils (persistent,
+// static round-robin); row CTAs host two units that only synchronise among themselves (named barriers).
+// What bounds them (profiles/r1b_experiments.txt): columns = TMA/L2 request path for 32-byte-inner boxes, rows =
+// shared-memory/LSU pipe; the FP64 butterflies are (almost) hidden under the data movement.
 // Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
 #include "tfft_kernels.cuh"
 
@@ -242,8 +244,7 @@ __device__ __forceinline__ double u8_to_double(unsigned v) {
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
 template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256>
 __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
-                                       const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/,
-                                       const double2* w1pre /*per-thread constants hoisted by the caller when J1 <= 2*/) {
+                                       const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/) {
     using G = Geo<LOG2N, VEC>;
 #pragma unroll
     for (int j = 0; j < G::J1; j++) {
@@ -264,13 +265,8 @@ __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2*
             }
         }
         dft<S, G::R1>(x);
-        double2 w1;
-        if constexpr (false) {
-            w1 = w1pre[j];
-        } else {
-            w1 = tw[(size_t)m << (TW_LOG2 - LOG2N)];
-            if (S < 0) w1.y = -w1.y;
-        }
+        double2 w1 = tw[(size_t)m << (TW_LOG2 - LOG2N)];
+        if (S < 0) w1.y = -w1.y;
         twiddle<G::R1>(x, w1);
 #pragma unroll
         for (int k = 0; k < G::R1; k++) L[(k * 256 + m) * VEC + c] = x[oidx<G::R1>(k)];
@@ -284,8 +280,7 @@ template <int S, int LOG2N, int VEC>
 struct ThreadTw {
     const double2* tw;
     int tt;
-    const double2* s1;  // unused placeholder (stage 1 loads its own)
-    __device__ __forceinline__ void load(const double2* __restrict__ t, int tt_) { tw = t; tt = tt_; s1 = nullptr; }
+    __device__ __forceinline__ void load(const double2* __restrict__ t, int tt_) { tw = t; tt = tt_; }
     __device__ __forceinline__ double2 s2v() const {
         double2 w = tw[(size_t)(tt & 15) << (TW_LOG2 - 8)];
         if (S < 0) w.y = -w.y;
@@ -415,7 +410,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, VEC>::UT* UNITS, 1) pencil_c2c(C2CA
     for (; item < a.nitems; item += stride) {
         cp_async_wait_all();
         unit_bar(bar_id, G::UT);
-        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
+        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1);
         unit_bar(bar_id, G::UT);
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
@@ -485,7 +480,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma(const __grid_constant__
     for (; item < a.nitems; item += stride) {
         mbar_wait(&full_bar, parity);
         parity ^= 1;
-        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
+        stage1<S, LOG2N, VEC, false>(L, tt, c, a.tw, nullptr, 0, 0, -1);
         __syncthreads();
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
@@ -590,7 +585,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     unsigned parity = 0;
     for (; item < a.nitems; item += stride, parity ^= 1) {
         mbar_wait(&full_bar, parity);
-        stage1<S, LOG2N, VEC, false, NZ>(L, tt, c, a.tw, nullptr, 0, 0, -1, ttw.s1);
+        stage1<S, LOG2N, VEC, false, NZ>(L, tt, c, a.tw, nullptr, 0, 0, -1);
         __syncthreads();
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
@@ -727,7 +722,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd(U8A
         const int y = (int)(item % a.H);
         const uint8_t* urow = U[buf] + ((img_base + (size_t)item * row_bytes) & 15);
         for (int ch = 0; ch < 3; ch++) {
-            stage1<+1, LOG2N, 1, true>(L, tt, 0, a.tw, urow, a.W, ch, a.center ? (y & 1) : -1, ttw.s1);
+            stage1<+1, LOG2N, 1, true>(L, tt, 0, a.tw, urow, a.W, ch, a.center ? (y & 1) : -1);
             unit_bar(bar_id, G::UT);
             double2 x[16];
             stage2_load<LOG2N, 1>(L, tt, 0, x);
@@ -789,7 +784,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv(U8A
         for (int ch = 0; ch < 3; ch++) {
             cp_async_wait_all();
             unit_bar(bar_id, G::UT);
-            stage1<-1, LOG2N, 1, false>(L, tt, 0, a.tw, nullptr, 0, 0, -1, ttw.s1);
+            stage1<-1, LOG2N, 1, false>(L, tt, 0, a.tw, nullptr, 0, 0, -1);
             unit_bar(bar_id, G::UT);
             double2 x[16];
             stage2_load<LOG2N, 1>(L, tt, 0, x);
