@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""BASELINE configs 2 and 4 on one GPU (config 1 is the cross-tool CLI test, config 3 is bench.py, config 5 is
+"""BASELINE configs 1, 2 and 4 on one GPU (config 3 is bench.py, config 5 is
 tools/run_c5.py).  Prints one JSON line per case.
 
+    python tools/run_configs.py c1            # 512x512 PNG through both CLIs (ours and the stock reference), all four ways
     python tools/run_configs.py c2            # 1080p (pad 2048^2) and 2048^2 single-image embed+extract, ~8 KB payload
     python tools/run_configs.py c4            # extract-only sweep 512^2 .. 8192^2 over stego batches made by our embed
 
@@ -48,6 +49,41 @@ def wall_time(fn, reps):
         fn()
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) * 1e3 / reps
+
+
+def c1():
+    """Config 1: 512x512 PNG, "the eagle has landed", default alpha/density, through the two CLIs (process start, PNG,
+    KDF and -- for ours -- CUDA context creation included), all four embed/extract combinations, pbkdf2_iter matched."""
+    import subprocess
+    import tempfile
+    from oracle import pyoracle
+    ours = os.path.join(ROOT, "steganosaurus_b200", "turtlefft")
+    ref = pyoracle.REF_CLI
+    d = tempfile.mkdtemp(prefix="tfft_c1_")
+    cover = os.path.join(d, "cover.png")
+    host.png_save(cover, synth.gen_cover(512, 512, 7))
+    for iters in (1000, 600000):
+        common = ["--pass", PW_.decode(), "--pbkdf2_iter", str(iters)]
+        res = {"config": f"C1 512x512 RGB PNG, 'the eagle has landed', CLI embed+extract, pbkdf2_iter {iters}"}
+        stego = {}
+        for name, exe in (("ours", ours), ("reference", ref)):
+            if not os.path.exists(exe):
+                res[name] = "not built"
+                continue
+            stego[name] = os.path.join(d, f"{name}_{iters}.png")
+            t0 = time.perf_counter()
+            p1 = subprocess.run([exe, "embed", "--in", cover, "--out", stego[name], "--secret", "the eagle has landed", *common], capture_output=True, text=True)
+            t1 = time.perf_counter()
+            p2 = subprocess.run([exe, "extract", "--in", stego[name], *common], capture_output=True, text=True)
+            t2 = time.perf_counter()
+            res[name] = {"embed_s": round(t1 - t0, 3), "extract_s": round(t2 - t1, 3), "embed_rc": p1.returncode,
+                         "recovered": "the eagle has landed" in p2.stdout}
+        if len(stego) == 2:  # cross: each tool reads the other's file
+            x1 = subprocess.run([ours, "extract", "--in", stego["reference"], *common], capture_output=True, text=True)
+            x2 = subprocess.run([ref, "extract", "--in", stego["ours"], *common], capture_output=True, text=True)
+            res["ours_reads_reference"] = "the eagle has landed" in x1.stdout
+            res["reference_reads_ours"] = "the eagle has landed" in x2.stdout
+        print(json.dumps(res), flush=True)
 
 
 def c2(ctx, check_oracle):
@@ -159,10 +195,12 @@ def c4(ctx, sizes):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c2", "c4"])
+    ap.add_argument("which", choices=["c1", "c2", "c4"])
     ap.add_argument("--sizes", default="512,1024,2048,4096,8192")
     ap.add_argument("--no-oracle", action="store_true")
     a = ap.parse_args()
+    if a.which == "c1":
+        return c1()
     with sb.Context(0) as ctx:
         if a.which == "c2":
             c2(ctx, not a.no_oracle)
