@@ -356,7 +356,7 @@ def run_ours(args):
             tj = json.load(open(tpath))
             if tj.get("kernel") == name and groups:
                 # ncu-measured DRAM bytes per image x images in one launch group of this run
-                traffic = tj["dram_bytes_per_image"] * (B * args.steps * (2 if name in ("row_fwd_u8", "col_fwd") else 1)) / groups
+                traffic = tj["dram_bytes_per_image"] * (nbytes / groups) / tj["algorithmic_bytes_per_image"]
         except Exception:
             pass
     mp_per_step = B * W * H / 1e6   # per rank; every rank runs the same batch size (weak scaling)

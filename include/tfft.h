@@ -26,7 +26,8 @@
  * Environment switches (read once; the defaults are the fast paths and none changes a result beyond
  * rounding): TFFT_FFT_IMPL=v0|lsu (baseline shared-memory kernel / cp.async column kernel),
  * TFFT_SPECTRUM=full (no Hermitian halving), TFFT_WIDE=0 (8192-pixel rows and tall images on the
- * unfused four-step path), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
+ * unfused four-step path), TFFT_COL_SAMPLE=0 (median sample by a separate gather pass),
+ * TFFT_EXTRACT_WINDOW=0 (extract transforms every column and keeps every row), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
  * images per chunk, chunks in flight), TFFT_PINGPONG=1, TFFT_ROW_UNITS=1, TFFT_SCAN_CTAS (experiments).
  */
 #ifndef TFFT_H
@@ -97,7 +98,10 @@ int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, in
  * majority vote over `rep` consecutive bins (rep3/rep7_decode_bits S:468/S:501; rep=1: none)
  * and MSB-first packing (bytes_from_bits S:447).
  *   out_bytes  [n][ceil(floor(nbins/rep)/8)] decoded bytes (may be NULL)
- *   raw_bits   [n][nbins] pre-vote bits (may be NULL) */
+ *   raw_bits   [n][nbins] pre-vote bits (may be NULL)
+ * The forward column pass of an extract only covers the part of the spectrum the bin list reads (the walk stays
+ * inside r <= rmax*min(PH,PW), S:771-774).  The _dev variants reduce the bin list on the device for that and
+ * synchronise `stream` ONCE at entry to read the two numbers back; everything after it is enqueued only. */
 int tfft_extract_bits(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
                       const uint32_t* bins, size_t nbins, int rep, const double* jitter,
                       double alpha, int center, uint8_t* out_bytes, uint8_t* raw_bits);
@@ -157,7 +161,8 @@ enum {
     TFFT_K_ROW_INV = 5,  /* row IFFT + scale/round/clamp/interleave/crop epilogue */
     TFFT_K_EXTRACT = 6,  /* phase gather + vote + pack */
     TFFT_K_C2C = 7,      /* plain c64 pass from the fft2d / fft_pass hooks */
-    TFFT_K_COUNT = 8
+    TFFT_K_COL_FWD_WIN = 8, /* column FFT of an extract: only the columns / rows that hold bins */
+    TFFT_K_COUNT = 9
 };
 int tfft_profile_enable(tfft_ctx* ctx, int on);
 int tfft_profile_reset(tfft_ctx* ctx);

@@ -48,7 +48,11 @@ struct tfft_ctx {
     uint64_t launches = 0;
     int fft_impl = 1;
     bool use_half = true;   // real-input symmetry (half-spectrum workspace); TFFT_SPECTRUM=full disables
+    bool col_sample = true; // median sample dropped by the forward column pass (TFFT_COL_SAMPLE=0: separate gather kernel)
     bool use_wide = true;   // 8192-pixel rows on the half-spectrum path; TFFT_WIDE=0 keeps them on the unfused four-step path
+    bool use_window = true; // extract: the forward column pass keeps only the rows / columns that hold bins (TFFT_EXTRACT_WINDOW=0: all)
+    unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
+    unsigned* h_win = nullptr;  // ... and read back through this pinned pair
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
     SpecLayout res_lay{0, 0, 0, 0};
     // resident spectra for the two-phase extract
@@ -246,11 +250,18 @@ int c2c_two_passes(tfft_ctx* ctx, const Launcher& L, PassArgs a, double2* spec, 
     return TFFT_OK;
 }
 
+// Part of the workspace an extract reads: stored rows < rows, stored columns < cols (0: unknown -> everything).  The
+// reference's walk only visits the quarter annulus r <= rmax * min(PH, PW) next to index (0,0) (S:771-774), so the
+// forward column pass of an extract neither transforms the columns nor stores the rows beyond it.
+struct BinWindow { int rows = 0, cols = 0; };
+
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
 // `where` (optional) receives the buffer that holds the spectrum afterwards: spec, or tmp when the four-step column
 // pass of a tall half-spectrum workspace left its result in the scratch batch (no copy back)
+// `sample_q` (optional, embed only): the 4096-point column pass drops its median sample there (col_pass_samples() > 0).
 int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center,
-                   double2** where = nullptr) {
+                   double2** where = nullptr, unsigned long long* sample_q = nullptr, unsigned sample_stride = 0,
+                   const BinWindow* win = nullptr) {
     if (where) *where = spec;
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     if (g.large) {  // unfused: u8 -> planes (zero pad materialised), then two generic c2c passes
@@ -277,7 +288,16 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         if (where) *where = tmp;
         return TFFT_OK;
     }
-    { ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD, (double)nimg * 3.0 * 16.0 * ((double)g.H * cols + (double)g.PH * cols)); CK(launch_fft_pass(L, a)); }
+    a.sample_q = sample_q; a.sample_stride = sample_stride;
+    double out_rows = (double)g.PH, ncols = cols;
+    int kind = TFFT_K_COL_FWD;
+    if (win && ctx->use_window && win->rows > 0 && win->cols > 0 && (win->rows < g.PH || win->cols < g.ld)) {
+        a.out_rows = std::min(g.PH, win->rows);
+        a.col_limit = std::min(g.ld, win->cols);
+        out_rows = (double)a.out_rows; ncols = (double)a.col_limit;
+        kind = TFFT_K_COL_FWD_WIN;
+    }
+    { ProfScope ps(ctx, L.stream, kind, (double)nimg * 3.0 * 16.0 * ((double)g.H * ncols + out_rows * ncols)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -317,14 +337,18 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
                 double alpha, int center, double magmin, double rmin, double rmax,
                 uint8_t* d_stego, uint64_t* d_usable, double* d_median) {
     double2* spec = nullptr;  // whichever of the slot's two buffers holds the spectrum
-    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec);
-    if (rc) return rc;
-    double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, cand_cap_for(g.P));
+    // the 4096-point forward column kernel can drop the median sample while its results are still on chip
+    unsigned presampled = (ctx->col_sample && !g.col4 && g.lh == 12 && g.half && ctx->fft_impl == 1) ? col_pass_samples(g.PH, g.PW, g.half) : 0;
+    if (presampled > mw.cand_cap) presampled = 0;
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec,
+                            presampled ? (unsigned long long*)mw.cand : nullptr, presampled ? mw.cand_cap : 0);
+    if (rc) return rc;
+    double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     const int m = std::min(g.PH, g.PW);
     { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.E);
-      CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable)); }
+      CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable, presampled)); }
     { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
       CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
     return inverse_images(ctx, L, spec, other, d_stego, nimg, g, center);
@@ -333,9 +357,9 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
 // nhdr == 0: one segment of `rep`; nhdr > 0: rep-3 header segment + rep-7 payload segment (S:1223-1268)
 int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_stego, int nimg, const Geom& g,
                   const uint32_t* d_bins, size_t nbins, int rep, size_t nhdr, const double* d_jitter, double alpha, int center,
-                  uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw) {
+                  uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw, const BinWindow& win) {
     double2* spec = nullptr;
-    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec);
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, nullptr, 0, &win);
     if (rc) return rc;
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
@@ -379,6 +403,32 @@ bool bins_ok(const uint32_t* bins, size_t n, size_t P) {
     for (size_t i = 0; i < n; i++)
         if ((bins[i] >> 30) > 2 || (size_t)(bins[i] & 0x3FFFFFFFu) >= P) return false;
     return true;
+}
+// the same check plus the window of the workspace the list touches (same rule as the bins_window kernel)
+bool bins_ok_window(const uint32_t* bins, size_t n, const Geom& g, BinWindow& w) {
+    uint32_t bad = 0;
+    int ry = 0, rx = 0;
+    const uint32_t P = (uint32_t)std::min<size_t>(g.P, 0x40000000u);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t lin = bins[i] & 0x3FFFFFFFu;
+        bad |= (uint32_t)((bins[i] >> 30) > 2) | (uint32_t)(lin >= P);
+        int y = (int)(lin >> g.lw), x = (int)(lin & (uint32_t)(g.PW - 1));
+        if (g.half && x > (g.PW >> 1)) { y = (g.PH - y) & (g.PH - 1); x = g.PW - x; }
+        ry = std::max(ry, y + 1);
+        rx = std::max(rx, x + 1);
+    }
+    w.rows = ry; w.cols = rx;
+    return !bad;
+}
+// device bin list: reduce on the device, read the two numbers back (one stream synchronisation per call)
+int bins_window_dev(tfft_ctx* ctx, const Launcher& L, const uint32_t* d_bins, size_t nbins, const Geom& g, BinWindow& w) {
+    w = BinWindow{};
+    if (!ctx->use_window || nbins == 0 || g.large || g.col4) return TFFT_OK;
+    CK(launch_bins_window(L, d_bins, nbins, g.lay(), ctx->d_win));
+    CK(cudaMemcpyAsync(ctx->h_win, ctx->d_win, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, L.stream));
+    CK(cudaStreamSynchronize(L.stream));
+    w.rows = (int)ctx->h_win[0]; w.cols = (int)ctx->h_win[1];
+    return TFFT_OK;
 }
 
 }  // namespace
@@ -432,10 +482,14 @@ int tfft_create(int device, tfft_ctx** out) {
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
     if (const char* wd = getenv("TFFT_WIDE")) ctx->use_wide = atoi(wd) != 0;
+    if (const char* cs = getenv("TFFT_COL_SAMPLE")) ctx->col_sample = atoi(cs) != 0;
+    if (const char* ew = getenv("TFFT_EXTRACT_WINDOW")) ctx->use_window = atoi(ew) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
     if (e == cudaSuccess) e = build_twiddles(ctx->d_tw, ctx->slot[0].stream);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_win, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_win, 2 * sizeof(unsigned), cudaHostAllocDefault);
     if (e != cudaSuccess) { tfft_destroy(ctx); cudaGetLastError(); return TFFT_E_CUDA; }
     *out = ctx;
     return TFFT_OK;
@@ -456,6 +510,8 @@ void tfft_destroy(tfft_ctx* ctx) {
     prof_drain(ctx);
     for (cudaEvent_t ev : ctx->prof_pool) cudaEventDestroy(ev);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
+    if (ctx->d_win) cudaFree(ctx->d_win);
+    if (ctx->h_win) cudaFreeHost(ctx->h_win);
     delete ctx;
 }
 
@@ -480,7 +536,7 @@ int tfft_profile_read(tfft_ctx* ctx, int kind, uint64_t* groups, double* total_m
 }
 const char* tfft_kind_name(int kind) {
     static const char* names[TFFT_K_COUNT] = {"row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter",
-                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass"};
+                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window"};
     return (kind >= 0 && kind < TFFT_K_COUNT) ? names[kind] : "?";
 }
 
@@ -596,12 +652,14 @@ static int extract_dev_impl(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W,
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
     const size_t nb = nhdr ? dec_bytes(nhdr, 3) : dec_bytes(nbins, rep);
     const size_t nbp = nhdr ? dec_bytes(nbins - nhdr, 7) : 0;
+    BinWindow win;
+    if ((rc = bins_window_dev(ctx, L, d_bins, nbins, g, win))) return rc;
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);
         rc = extract_chunk(ctx, L, S, d_stego + (size_t)i0 * g.img_bytes, m, g, d_bins, nbins, rep, nhdr, d_jitter, alpha, center,
                            d_out ? d_out + (size_t)i0 * nb : nullptr,
                            d_out_payload ? d_out_payload + (size_t)i0 * nbp : nullptr,
-                           d_raw_bits ? d_raw_bits + (size_t)i0 * nbins : nullptr);
+                           d_raw_bits ? d_raw_bits + (size_t)i0 * nbins : nullptr, win);
         if (rc) return rc;
     }
     return TFFT_OK;
@@ -615,7 +673,8 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
     int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
-    if (!bins_ok(bins, nbins, g.P)) return TFFT_E_INVALID;
+    BinWindow win;
+    if (!bins_ok_window(bins, nbins, g, win)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
     const int chunk = std::min(chunk_for(ctx, g, n, HOST_SLOTS), HOST_CHUNK);
@@ -653,7 +712,7 @@ static int extract_host_impl(tfft_ctx* ctx, const uint8_t* stego, int n, int W, 
         uint8_t* d_pay = out_payload ? (uint8_t*)S.outbytes.p + (out ? (size_t)chunk * nb : 0) : nullptr;
         rc = extract_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, nbins, rep, nhdr,
                            jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, d_out, d_pay,
-                           raw_bits ? (uint8_t*)S.raw.p : nullptr);
+                           raw_bits ? (uint8_t*)S.raw.p : nullptr, win);
         if (rc) return rc;
         if (d_out && nb) CK(cudaMemcpyAsync(S.h_stage, d_out, (size_t)m * nb, cudaMemcpyDeviceToHost, st));
         if (d_pay && nbp) CK(cudaMemcpyAsync(S.h_stage + (out ? (size_t)chunk * nb : 0), d_pay, (size_t)m * nbp, cudaMemcpyDeviceToHost, st));

@@ -5,6 +5,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -506,7 +507,7 @@ __global__ void median_bracket_all(MedianWork w, int nplanes, Bracket* br) {
 // The bracket only has to CONTAIN the median, so the two order statistics are resolved to the
 // top 22 key bits (exponent + 11 mantissa bits, 0.05 % in magnitude) with two histogram passes
 // over the sample and then rounded outwards.
-__global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, Bracket* br) {
+__global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S, Bracket* br, int qkeys) {
     __shared__ uint32_t h1[RADIX], h2lo[RADIX], h2hi[RADIX];
     __shared__ uint32_t s_blo, s_bhi, s_rlo, s_rhi, s_slo, s_shi;
     const int ip = blockIdx.x;
@@ -566,8 +567,9 @@ __global__ void __launch_bounds__(1024) median_bracket(MedianWork w, uint32_t S,
         const uint64_t klo = ((uint64_t)blo << 52) | ((uint64_t)s_slo << 41);                              // lower edge
         const uint64_t khi = ((((uint64_t)bhi << 11) | (uint64_t)s_shi) + 1 << 41) - 1;                      // upper edge
         const double lo = __longlong_as_double((long long)klo), hi = __longlong_as_double((long long)khi);
-        br[ip].qlo = lo * lo * (1.0 - 1e-9);
-        br[ip].qhi = (khi >= 0x7ff0000000000000ull) ? __longlong_as_double(0x7ff0000000000000LL) : hi * hi * (1.0 + 1e-9);
+        // keys are magnitudes (gathered sample) or already q = |F|^2 (sample dropped by the column pass)
+        br[ip].qlo = (qkeys ? lo : lo * lo) * (1.0 - 1e-9);
+        br[ip].qhi = (khi >= 0x7ff0000000000000ull) ? __longlong_as_double(0x7ff0000000000000LL) : (qkeys ? hi : hi * hi) * (1.0 + 1e-9);
         w.cand_n[ip] = 0;  // becomes the member fill counter
     }
 }
@@ -820,7 +822,7 @@ static uint64_t annulus_total_host(int PH, int PW, int ymax, int xmax, double rl
 
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable) {
+                                   double* d_median, uint64_t* d_usable, unsigned presampled) {
     const int PH = lay.PH, PW = lay.PW;
     const uint64_t P = (uint64_t)PH * PW;        // size of the full multiset (ranks refer to it)
     const uint64_t E = lay.plane_elems();        // stored elements per plane
@@ -832,13 +834,16 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     if (all) {
         median_bracket_all<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, nplanes, br);
         TFFT_LAUNCH_CHECK(L);
+    } else if (presampled && presampled <= w.cand_cap) {
+        median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, presampled, br, 1);
+        TFFT_LAUNCH_CHECK(L);
     } else {
         const uint64_t logical = lay.half ? P / 2 : P;
         const uint32_t S = SAMPLE_MAX < w.cand_cap ? SAMPLE_MAX : w.cand_cap;
         const uint64_t stride = logical / S;
         median_sample<<<dim3((S + 255) / 256 > 256 ? 256 : (S + 255) / 256, (unsigned)nplanes), 256, 0, L.stream>>>(spec, lay, S, stride, w);
         TFFT_LAUNCH_CHECK(L);
-        median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, br);
+        median_bracket<<<nplanes, 1024, 0, L.stream>>>(w, S, br, 0);
         TFFT_LAUNCH_CHECK(L);
     }
     int ymax = (int)floor(rhi), xmax = (int)floor(rhi);
@@ -1003,6 +1008,30 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
     const int lane = threadIdx.x & 31;
     const size_t byte0 = (d - lane) / 8;
     if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
+}
+
+// Window of the workspace a bin list touches: out[0] = 1 + largest stored row, out[1] = 1 + largest stored column
+// (half layout: a bin right of the Nyquist column is read through its mirror, spec_load).  out must be zeroed.
+__global__ void __launch_bounds__(256) bins_window(const uint32_t* __restrict__ bins, size_t nbins, SpecLayout lay, unsigned* out) {
+    unsigned ry = 0, rx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t lin = bins[i] & 0x3FFFFFFFu;
+        int y = (int)(lin / (uint32_t)lay.PW), x = (int)(lin % (uint32_t)lay.PW);
+        if (lay.half && x > (lay.PW >> 1)) { y = (lay.PH - y) & (lay.PH - 1); x = lay.PW - x; }
+        ry = max(ry, (unsigned)y + 1u);
+        rx = max(rx, (unsigned)x + 1u);
+    }
+    ry = __reduce_max_sync(0xffffffffu, ry);
+    rx = __reduce_max_sync(0xffffffffu, rx);
+    if ((threadIdx.x & 31) == 0) { atomicMax(out, ry); atomicMax(out + 1, rx); }
+}
+cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t nbins, SpecLayout lay, unsigned* d_out2) {
+    cudaError_t e = cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned), L.stream);
+    if (e != cudaSuccess || nbins == 0) return e;
+    const unsigned grid = (unsigned)std::min<size_t>((nbins + 255) / 256, 4 * (size_t)L.sm_count);
+    bins_window<<<grid, 256, 0, L.stream>>>(bins, nbins, lay, d_out2);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
 }
 
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout P,

@@ -32,6 +32,8 @@ struct PassArgs {
     int in_rows;  // plane rows y >= in_rows are all-zero on input and are NOT read
                   //   (axis 0: such pencils are skipped; axis 1: those elements are zero-filled)
     int out_rows; // plane rows y >= out_rows are not needed downstream and are NOT written
+    int col_limit; // axis 1 only, 0 = all: columns x >= col_limit (rounded up to the kernel's column group) are not needed
+                   //   downstream and are neither read nor transformed (extract: the bins sit in a corner of the plane)
     // Half-spectrum mode (real planes): the workspace keeps columns 0..PW/2 with row stride ld =
     // PW/2 + 16.  u8 passes get half = 1 (PW = full width, ld = stride); column passes simply see a
     // plane of PW := ld columns.
@@ -41,7 +43,14 @@ struct PassArgs {
     // (four-step scheme: strided 4096-point sub-transforms in place, radix-2/4 combine through tmp).
     double2* tmp;
     int leave_in_tmp;  // four-step passes only: skip the copy back, the result stays in tmp (the caller ping-pongs)
+    // Forward 4096-point column pass only (optional): the kernel drops a stratified sample of q = re^2 + im^2 (one
+    // element per thread and column pair, as IEEE bit patterns) into sample_q[plane * sample_stride + ...] -- the
+    // median bracket is then built from it without a separate gather pass over the spectrum.
+    unsigned long long* sample_q;
+    unsigned sample_stride;
 };
+// number of samples per plane the 4096-point column pass delivers for a half-spectrum plane of PW columns (0: none)
+inline unsigned col_pass_samples(int PH, int PW_full, int half) { return (PH == 4096 && half) ? (unsigned)(PW_full / 4) * 256u : 0u; }
 
 // How a plane's spectrum is stored.  full: [PH][PW], ld = PW.  half (real planes, Hermitian):
 // columns 0..PW/2 only, row stride ld = PW/2 + 16 (pad columns are zero); element (y,x) with
@@ -87,9 +96,10 @@ constexpr uint32_t CAND_B_MAX = 1u << 15;
 size_t median_work_bytes(int nplanes, uint32_t cand_cap);
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);
 // d_median: [nplanes]; d_usable: [nplanes/3] (sum over the 3 planes of count/2)
+// presampled > 0: w.cand already holds that many q-keys per plane (written by the column pass), no gather pass
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable);
+                                   double* d_median, uint64_t* d_usable, unsigned presampled = 0);
 
 // ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
 cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,
@@ -100,6 +110,9 @@ cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout 
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout lay,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
                            uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+
+// window of the workspace a bin list touches: d_out2[0] = 1 + largest stored row, d_out2[1] = 1 + largest stored column
+cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t nbins, SpecLayout lay, unsigned* d_out2);
 
 // unfused image <-> plane conversion for sizes the fused row passes do not cover (PW or PH > 4096)
 cudaError_t launch_u8_to_planes(const Launcher& L, const uint8_t* img, double2* spec, int nimg, int W, int H, int PW, int PH, int center);

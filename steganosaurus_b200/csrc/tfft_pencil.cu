@@ -441,6 +441,11 @@ struct ColTmaArgs {
     const double2* tw;
     long long nitems;      // nplanes * PW / VEC
     int groups_per_plane;  // PW / VEC
+    // pencil_col_tma_w, forward only: stratified sample of q = |F|^2 for the median bracket (null: off).  Column pairs
+    // g < sample_groups each contribute 256 values: thread (k1, m) of column g & 1 picks one of its 16 row blocks by hash.
+    unsigned long long* sample_q;
+    unsigned sample_stride;   // entries per plane
+    int sample_groups;        // column pairs that hold interior columns (PW_full / 4)
 };
 
 template <int S, int LOG2N, int VEC>
@@ -549,6 +554,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     //   xfree_b (1)             the first half has been read out         -> everybody may stage the second half
     // The three duties sit in three different warps, so no single warp carries all the waiting.
     constexpr int TL = 0, TS0 = 160, TS1 = 320;
+    constexpr int TLAST = K3N > 8 ? TS1 : TS0;  // the thread that issues a pair's last store
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t full_bar, lfree, xfree_a, xfree_b, staged0, staged1;
     double2* L = (double2*)smem_raw;
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
         mbar_arrive(&lfree);
-        if (tid == TS1) {  // its own store of the previous pair's second half has finished reading X
+        if (tid == TLAST) {  // its own store of the previous pair's last half has finished reading X
             tma_wait_read_all();
             mbar_arrive(&xfree_a);
         }
@@ -626,6 +632,13 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
             v.x *= scale; v.y *= scale;
             Sw[(k3 * 16 + m) * VEC + c] = v;
         }
+        // median sample: this thread's row block for this pair, read back from its own staging entries
+        const bool samp = S > 0 && a.sample_q != nullptr && g < a.sample_groups && c == (g & 1);
+        const unsigned k3s = (((unsigned)tt * 2654435761u) >> 15 ^ ((unsigned)g * 0x9E3779B9u) >> 11 ^ (unsigned)plane * 7u) & 15u;
+        if (samp && k3s < 8 && (int)k3s < K3N) {
+            const double2 v = Sw[(k3s * 16 + m) * VEC + c];
+            a.sample_q[(size_t)plane * a.sample_stride + (size_t)g * 256 + tt] = (unsigned long long)__double_as_longlong(fma(v.x, v.x, v.y * v.y));
+        }
         fence_async_proxy();
         mbar_arrive(&staged0);
         if (tid == TS0) {
@@ -633,8 +646,10 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
             // smem image [k1][k3][k2][2 columns] -> rows k1 + 16 k2 + 256 k3 (map dims: col, k2, k3, k1, plane)
             tma_store_5d(&out_map, X, g * VEC * 2, 0, 0, 0, plane);
             tma_commit();
-            tma_wait_read_all();
-            mbar_arrive(&xfree_b);
+            if constexpr (K3N > 8) {  // (K3N <= 8: this was the last store of the pair, TS0 waits for it at the top of the next one)
+                tma_wait_read_all();
+                mbar_arrive(&xfree_b);
+            }
         }
         // ---- second half: rows with 8 <= k3 < K3N
         if constexpr (K3N > 8) {
@@ -645,6 +660,10 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
                 double2 v = z[oidx<16>(k3)];
                 v.x *= scale; v.y *= scale;
                 Sw[((k3 - 8) * 16 + m) * VEC + c] = v;
+            }
+            if (samp && k3s >= 8 && (int)k3s < K3N) {
+                const double2 v = Sw[((k3s - 8) * 16 + m) * VEC + c];
+                a.sample_q[(size_t)plane * a.sample_stride + (size_t)g * 256 + tt] = (unsigned long long)__double_as_longlong(fma(v.x, v.x, v.y * v.y));
             }
             fence_async_proxy();
             mbar_arrive(&staged1);
@@ -1301,6 +1320,14 @@ bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int P
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// column groups of `vec` columns a pass has to transform (PassArgs::col_limit trims the right-hand side of the plane)
+inline int col_groups(const PassArgs& p, int vec) {
+    const int all = p.PW / vec;
+    if (p.col_limit <= 0) return all;
+    const int need = (p.col_limit + vec - 1) / vec;
+    return need < all ? need : all;
+}
+
 template <int S, int NZ, int K3N>
 cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     using G = pk::Geo<12, 2>;
@@ -1309,7 +1336,10 @@ cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
           make_col_store_map5(&out_map, p.spec, p.nplanes, p.PH, p.PW, p.out_rows);
     if (!*ok) return cudaSuccess;
     pk::ColTmaArgs a;
-    a.tw = p.tw; a.groups_per_plane = p.PW / 2; a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    a.tw = p.tw; a.groups_per_plane = col_groups(p, 2); a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    a.sample_q = S > 0 ? p.sample_q : nullptr;
+    a.sample_stride = p.sample_stride;
+    a.sample_groups = (int)(p.sample_stride ? (p.PW - 16) / 2 : 0);  // p.PW is ld = PW_full/2 + 16 here: pairs below the Nyquist column
     const size_t smem = G::L_BYTES + G::X_BYTES;
     auto kern = pk::pencil_col_tma_w<S, NZ, K3N>;
     cudaError_t e = set_smem(kern, smem);
@@ -1327,7 +1357,8 @@ cudaError_t run_col_tma(const Launcher& L, const PassArgs& p, bool* ok) {
           make_col_map(&out_map, p.spec, p.nplanes, p.PH, p.PW, p.out_rows, VEC);
     if (!*ok) return cudaSuccess;
     pk::ColTmaArgs a;
-    a.tw = p.tw; a.groups_per_plane = p.PW / VEC; a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    a.tw = p.tw; a.groups_per_plane = col_groups(p, VEC); a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    a.sample_q = nullptr; a.sample_stride = 0; a.sample_groups = 0;
     const size_t smem = G::L_BYTES + G::X_BYTES;
     auto kern = pk::pencil_col_tma<S, LOG2N, VEC>;
     cudaError_t e = set_smem(kern, smem);
@@ -1418,9 +1449,11 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
         if (L.fft_impl != 2 && !blockk && p.PW >= 2) {
             bool ok = false;
             // zero structure of a padded image (UHD: 2160 of 4096 rows): 9 of 16 row blocks carry data
-            const bool few_in = p.in_rows <= 9 * 256, few_out = p.out_rows <= 9 * 256;
+            // forward pass of an extract: only the rows that hold bins are kept (the default annulus ends at row 0.45 * 4096)
+            const bool few_in = p.in_rows <= 9 * 256, few_out = p.out_rows <= 9 * 256, half_out = p.out_rows <= 8 * 256;
             cudaError_t e = p.inverse ? (few_out ? run_col_tma_w<-1, 16, 9>(L, p, &ok) : run_col_tma_w<-1, 16, 16>(L, p, &ok))
-                                      : (few_in ? run_col_tma_w<+1, 9, 16>(L, p, &ok) : run_col_tma_w<+1, 16, 16>(L, p, &ok));
+                            : half_out ? (few_in ? run_col_tma_w<+1, 9, 8>(L, p, &ok) : run_col_tma_w<+1, 16, 8>(L, p, &ok))
+                                       : (few_in ? run_col_tma_w<+1, 9, 16>(L, p, &ok) : run_col_tma_w<+1, 16, 16>(L, p, &ok));
             if (e != cudaSuccess || ok) return e;
         }
     }

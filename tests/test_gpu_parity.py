@@ -117,6 +117,30 @@ def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
         assert np.array_equal(dec[0], wdec)
 
 
+@pytest.mark.parametrize("W,H", [(600, 4096), (1024, 700), (520, 3000), (300, 200)])
+def test_extract_window_any_bins(ctx, W, H):
+    """An extract only transforms the part of the spectrum its bin list reads (rows / columns beyond the last bin are
+    neither stored nor transformed).  Bin lists anywhere in the plane -- the annulus corner, the whole plane, right of
+    the Nyquist column (read through the Hermitian mirror), the last rows -- must give the oracle's bits."""
+    o = oracle()
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    img = synth.gen_texture(W, H, W + H)
+    rng = np.random.default_rng(W * 3 + H)
+    n = 4998
+    boxes = {"corner": (1, PH // 8, 1, PW // 8), "low_rows": (0, 3, 0, PW), "anywhere": (0, PH, 0, PW),
+             "right_half": (0, PH // 4, PW // 2 + 1, PW), "last_rows": (PH - 5, PH, 0, PW // 3), "one_bin": (7, 8, 9, 10)}
+    for name, (y0, y1, x0, x1) in boxes.items():
+        y = rng.integers(y0, y1, n).astype(np.uint32)
+        x = rng.integers(x0, x1, n).astype(np.uint32)
+        pl = rng.integers(0, 3, n).astype(np.uint32)
+        bins = (pl << np.uint32(30)) | (y * np.uint32(PW) + x)
+        for rep in (1, 7):
+            dec, raw = ctx.extract_bits(img[None], bins, rep)
+            wdec, wraw = o.extract(img, bins, rep)
+            assert np.array_equal(raw[0], wraw), (name, rep)
+            assert np.array_equal(dec[0], wdec), (name, rep)
+
+
 def test_batch_chunking_and_independence(ctx):
     """Every image has its own bits; a tiny workspace forces several chunks and both slots."""
     W = H = 128

@@ -61,7 +61,7 @@ def test_pipeline_embed_extract_on_gpu(tmp_path):
         assert [r.ok for r in emb] == [True] * 5 + [False]
         assert emb[5].error.startswith("Message too large. Need ")
         ext = pl.extract_files(outs[:5] + [covers[0]], PASS, prm)
-        assert [r.plaintext for r in ext[:5]] == secrets[:5]
+        assert [r.plaintext for r in ext[:5]] == secrets[:5], [(r.ok, r.error) for r in ext]
         assert not ext[5].ok and ext[5].error == "Magic not found."   # a clean cover carries nothing
         # the single-image path reads the pipeline's output, and the reference CLI does too
         assert host.extract_image(ctx, host.png_load(outs[2]), PASS, pbkdf2_iter=1000) == secrets[2]
