@@ -24,6 +24,7 @@ struct DevBuf {
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf spec, spec2, in, out, bits, med, medians, usable, outbytes, raw;  // spec2: scratch of the four-step passes (dims > 4096)
+    DevBuf signmap;  // extract without jitter on 4096-row planes: read bits of every element instead of the spectrum
     // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
     // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
     // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
@@ -51,6 +52,7 @@ struct tfft_ctx {
     bool col_sample = true; // median sample dropped by the forward column pass (TFFT_COL_SAMPLE=0: separate gather kernel)
     bool use_wide = true;   // 8192-pixel rows on the half-spectrum path; TFFT_WIDE=0 keeps them on the unfused four-step path
     bool use_window = true; // extract: the forward column pass keeps only the rows / columns that hold bins (TFFT_EXTRACT_WINDOW=0: all)
+    bool use_signmap = true; // extract without jitter, 4096-row planes: the column pass leaves read bits, not spectra (TFFT_SIGNMAP=0)
     unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
     unsigned* h_win = nullptr;  // ... and read back through this pinned pair
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
@@ -253,15 +255,24 @@ int c2c_two_passes(tfft_ctx* ctx, const Launcher& L, PassArgs a, double2* spec, 
 // Part of the workspace an extract reads: stored rows < rows, stored columns < cols (0: unknown -> everything).  The
 // reference's walk only visits the quarter annulus r <= rmax * min(PH, PW) next to index (0,0) (S:771-774), so the
 // forward column pass of an extract neither transforms the columns nor stores the rows beyond it.
-struct BinWindow { int rows = 0, cols = 0; };
+struct BinWindow { int rows = 0, cols = 0, mirrored = 0; };  // mirrored: some bin sits right of the Nyquist column of a half plane
+
+// optional extras of forward_images
+struct FwdOpts {
+    unsigned long long* sample_q = nullptr;  // embed, 4096-row half planes: the column pass drops the median sample here
+    unsigned sample_stride = 0;
+    const BinWindow* win = nullptr;          // extract: part of the workspace the bin list reads
+    uint32_t* signmap = nullptr;             // extract: leave read bits (for this alpha) instead of the column-pass spectrum
+    double alpha = 0.0;
+};
 
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
 // `where` (optional) receives the buffer that holds the spectrum afterwards: spec, or tmp when the four-step column
 // pass of a tall half-spectrum workspace left its result in the scratch batch (no copy back)
 // `sample_q` (optional, embed only): the 4096-point column pass drops its median sample there (col_pass_samples() > 0).
 int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp, const uint8_t* d_img, int nimg, const Geom& g, int center,
-                   double2** where = nullptr, unsigned long long* sample_q = nullptr, unsigned sample_stride = 0,
-                   const BinWindow* win = nullptr) {
+                   double2** where = nullptr, const FwdOpts& o = FwdOpts{}) {
+    const BinWindow* win = o.win;
     if (where) *where = spec;
     PassArgs a = base_args(ctx, spec, nimg, g, center);
     if (g.large) {  // unfused: u8 -> planes (zero pad materialised), then two generic c2c passes
@@ -288,7 +299,7 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         if (where) *where = tmp;
         return TFFT_OK;
     }
-    a.sample_q = sample_q; a.sample_stride = sample_stride;
+    a.sample_q = o.sample_q; a.sample_stride = o.sample_stride;
     double out_rows = (double)g.PH, ncols = cols;
     int kind = TFFT_K_COL_FWD;
     if (win && ctx->use_window && win->rows > 0 && win->cols > 0 && (win->rows < g.PH || win->cols < g.ld)) {
@@ -297,7 +308,12 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         out_rows = (double)a.out_rows; ncols = (double)a.col_limit;
         kind = TFFT_K_COL_FWD_WIN;
     }
-    { ProfScope ps(ctx, L.stream, kind, (double)nimg * 3.0 * 16.0 * ((double)g.H * ncols + out_rows * ncols)); CK(launch_fft_pass(L, a)); }
+    double out_bytes = 16.0 * out_rows * ncols;
+    if (o.signmap && kind == TFFT_K_COL_FWD_WIN) {  // (the caller checked the conditions: 4096 rows, window of at most 2048 rows)
+        a.signmap = o.signmap; a.sign_alpha = o.alpha;
+        out_bytes = out_rows * ncols / 8.0;
+    }
+    { ProfScope ps(ctx, L.stream, kind, (double)nimg * 3.0 * (16.0 * (double)g.H * ncols + out_bytes)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
 
@@ -342,8 +358,9 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     // the 4096-point forward column kernel can drop the median sample while its results are still on chip
     unsigned presampled = (ctx->col_sample && !g.col4 && g.lh == 12 && g.half && ctx->fft_impl == 1) ? col_pass_samples(g.PH, g.PW, g.half) : 0;
     if (presampled > mw.cand_cap) presampled = 0;
-    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec,
-                            presampled ? (unsigned long long*)mw.cand : nullptr, presampled ? mw.cand_cap : 0);
+    FwdOpts fo;
+    if (presampled) { fo.sample_q = (unsigned long long*)mw.cand; fo.sample_stride = mw.cand_cap; }
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec, fo);
     if (rc) return rc;
     double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     const int m = std::min(g.PH, g.PW);
@@ -359,8 +376,31 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
                   const uint32_t* d_bins, size_t nbins, int rep, size_t nhdr, const double* d_jitter, double alpha, int center,
                   uint8_t* d_out_bytes, uint8_t* d_out_payload, uint8_t* d_raw, const BinWindow& win) {
     double2* spec = nullptr;
-    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, nullptr, 0, &win);
+    FwdOpts fo;
+    fo.win = &win;
+    // Without jitter the read decision is a property of the element alone, so a 4096-row column pass can leave one bit
+    // per element instead of 16 bytes (window of at most 2048 rows, no bin behind the Nyquist column, alpha away from
+    // 0 and pi so that the decision is the sign of the imaginary part off the real axis).
+    const bool sign = ctx->use_signmap && ctx->use_window && !d_jitter && !g.large && !g.col4 && g.lh == 12 && nbins > 0 &&
+                      win.rows > 0 && win.rows <= 2048 && !win.mirrored && alpha >= 1e-6 && alpha <= 3.14159 && signmap_supported(L);
+    if (sign) {
+        int rc2 = ensure(ctx, S.signmap, (size_t)nimg * 3 * sign_map_words(g.ld) * sizeof(uint32_t));
+        if (rc2) return rc2;
+        fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha;
+    }
+    int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, fo);
     if (rc) return rc;
+    if (sign) {
+        const uint32_t* bm = (const uint32_t*)S.signmap.p;
+        ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (4.0 + 4.0));
+        if (nhdr == 0) {
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nbins, rep, d_out_bytes, d_raw, nbins));
+        } else {
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nhdr, 3, d_out_bytes, d_raw, nbins));
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins));
+        }
+        return TFFT_OK;
+    }
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
         CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins));
@@ -413,7 +453,7 @@ bool bins_ok_window(const uint32_t* bins, size_t n, const Geom& g, BinWindow& w)
         const uint32_t lin = bins[i] & 0x3FFFFFFFu;
         bad |= (uint32_t)((bins[i] >> 30) > 2) | (uint32_t)(lin >= P);
         int y = (int)(lin >> g.lw), x = (int)(lin & (uint32_t)(g.PW - 1));
-        if (g.half && x > (g.PW >> 1)) { y = (g.PH - y) & (g.PH - 1); x = g.PW - x; }
+        if (g.half && x > (g.PW >> 1)) { y = (g.PH - y) & (g.PH - 1); x = g.PW - x; w.mirrored = 1; }
         ry = std::max(ry, y + 1);
         rx = std::max(rx, x + 1);
     }
@@ -425,9 +465,9 @@ int bins_window_dev(tfft_ctx* ctx, const Launcher& L, const uint32_t* d_bins, si
     w = BinWindow{};
     if (!ctx->use_window || nbins == 0 || g.large || g.col4) return TFFT_OK;
     CK(launch_bins_window(L, d_bins, nbins, g.lay(), ctx->d_win));
-    CK(cudaMemcpyAsync(ctx->h_win, ctx->d_win, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, L.stream));
+    CK(cudaMemcpyAsync(ctx->h_win, ctx->d_win, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, L.stream));
     CK(cudaStreamSynchronize(L.stream));
-    w.rows = (int)ctx->h_win[0]; w.cols = (int)ctx->h_win[1];
+    w.rows = (int)ctx->h_win[0]; w.cols = (int)ctx->h_win[1]; w.mirrored = (int)ctx->h_win[2];
     return TFFT_OK;
 }
 
@@ -484,12 +524,13 @@ int tfft_create(int device, tfft_ctx** out) {
     if (const char* wd = getenv("TFFT_WIDE")) ctx->use_wide = atoi(wd) != 0;
     if (const char* cs = getenv("TFFT_COL_SAMPLE")) ctx->col_sample = atoi(cs) != 0;
     if (const char* ew = getenv("TFFT_EXTRACT_WINDOW")) ctx->use_window = atoi(ew) != 0;
+    if (const char* sm = getenv("TFFT_SIGNMAP")) ctx->use_signmap = atoi(sm) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
     if (e == cudaSuccess) e = build_twiddles(ctx->d_tw, ctx->slot[0].stream);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_win, 2 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_win, 2 * sizeof(unsigned), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_win, 3 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_win, 3 * sizeof(unsigned), cudaHostAllocDefault);
     if (e != cudaSuccess) { tfft_destroy(ctx); cudaGetLastError(); return TFFT_E_CUDA; }
     *out = ctx;
     return TFFT_OK;
@@ -502,7 +543,7 @@ void tfft_destroy(tfft_ctx* ctx) {
     for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
         release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.med);
-        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw);
+        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap);
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }

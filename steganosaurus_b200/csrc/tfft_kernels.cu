@@ -1010,23 +1010,71 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
     if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
 }
 
-// Window of the workspace a bin list touches: out[0] = 1 + largest stored row, out[1] = 1 + largest stored column
-// (half layout: a bin right of the Nyquist column is read through its mirror, spec_load).  out must be zeroed.
+// ---- the same two kernels reading the sign map the forward column pass of an extract left behind (PassArgs::signmap)
+__device__ __forceinline__ int map_bit(const uint32_t* __restrict__ bm, int groups, int img, int PW, uint32_t b) {
+    const uint32_t lin = b & 0x3FFFFFFFu;
+    const int y = (int)(lin / (uint32_t)PW), x = (int)(lin % (uint32_t)PW);
+    const size_t plane = (size_t)(img * 3 + (int)(b >> 30));
+    const uint32_t w = bm[((plane * groups + (x >> 1)) * 16 + (y & 15)) * 8 + (y >> 8)];
+    return (int)((w >> ((((y >> 4) & 15) << 1) | (x & 1))) & 1u);
+}
+__global__ void __launch_bounds__(256) extract_raw_map(const uint32_t* __restrict__ bm, int groups, int PW, const uint32_t* __restrict__ bins,
+                                                       size_t nbins, uint8_t* raw_bits, size_t raw_stride) {
+    const int img = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbins) return;
+    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)map_bit(bm, groups, img, PW, bins[i]);
+}
+__global__ void __launch_bounds__(256) extract_vote_map(const uint32_t* __restrict__ bm, int groups, int PW, const uint32_t* __restrict__ bins,
+                                                        size_t ndec, int rep, uint8_t* out_bytes, size_t nbytes) {
+    const int img = blockIdx.y;
+    const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bit = 0;
+    if (d < ndec) {
+        int s = 0;
+        for (int j = 0; j < rep; j++) s += map_bit(bm, groups, img, PW, bins[d * rep + j]);
+        bit = (s >= rep / 2 + 1) ? 1 : 0;
+    }
+    const unsigned m = __brev(__ballot_sync(0xffffffffu, bit));
+    const int lane = threadIdx.x & 31;
+    const size_t byte0 = (d - lane) / 8;
+    if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
+}
+cudaError_t launch_extract_signmap(const Launcher& L, const uint32_t* signmap, int cols, int nimg, SpecLayout lay,
+                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride) {
+    if (nimg == 0) return cudaSuccess;
+    const int groups = cols / 2;
+    if (raw_bits && nbins) {
+        extract_raw_map<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, nbins, raw_bits, raw_stride ? raw_stride : nbins);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    const size_t ndec = nbins / (size_t)rep;
+    const size_t nbytes = (ndec + 7) / 8;
+    if (out_bytes && nbytes) {
+        extract_vote_map<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, ndec, rep, out_bytes, nbytes);
+        TFFT_LAUNCH_CHECK(L);
+    }
+    return cudaSuccess;
+}
+
+// Window of the workspace a bin list touches: out[0] = 1 + largest stored row, out[1] = 1 + largest stored column,
+// out[2] = 1 when a bin is read through its mirror (half layout: bins right of the Nyquist column, spec_load).
 __global__ void __launch_bounds__(256) bins_window(const uint32_t* __restrict__ bins, size_t nbins, SpecLayout lay, unsigned* out) {
-    unsigned ry = 0, rx = 0;
+    unsigned ry = 0, rx = 0, mir = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t lin = bins[i] & 0x3FFFFFFFu;
         int y = (int)(lin / (uint32_t)lay.PW), x = (int)(lin % (uint32_t)lay.PW);
-        if (lay.half && x > (lay.PW >> 1)) { y = (lay.PH - y) & (lay.PH - 1); x = lay.PW - x; }
+        if (lay.half && x > (lay.PW >> 1)) { y = (lay.PH - y) & (lay.PH - 1); x = lay.PW - x; mir = 1; }
         ry = max(ry, (unsigned)y + 1u);
         rx = max(rx, (unsigned)x + 1u);
     }
     ry = __reduce_max_sync(0xffffffffu, ry);
     rx = __reduce_max_sync(0xffffffffu, rx);
-    if ((threadIdx.x & 31) == 0) { atomicMax(out, ry); atomicMax(out + 1, rx); }
+    mir = __reduce_max_sync(0xffffffffu, mir);
+    if ((threadIdx.x & 31) == 0) { atomicMax(out, ry); atomicMax(out + 1, rx); if (mir) atomicMax(out + 2, 1u); }
 }
 cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t nbins, SpecLayout lay, unsigned* d_out2) {
-    cudaError_t e = cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned), L.stream);
+    cudaError_t e = cudaMemsetAsync(d_out2, 0, 3 * sizeof(unsigned), L.stream);
     if (e != cudaSuccess || nbins == 0) return e;
     const unsigned grid = (unsigned)std::min<size_t>((nbins + 255) / 256, 4 * (size_t)L.sm_count);
     bins_window<<<grid, 256, 0, L.stream>>>(bins, nbins, lay, d_out2);

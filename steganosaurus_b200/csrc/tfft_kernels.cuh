@@ -48,7 +48,14 @@ struct PassArgs {
     // median bracket is then built from it without a separate gather pass over the spectrum.
     unsigned long long* sample_q;
     unsigned sample_stride;
+    // Forward 4096-point column pass of an extract without jitter (optional, out_rows <= 2048): instead of the spectrum
+    // the pass leaves one bit per element -- what read_bit_from_bin (S:734-746) reads there with this alpha -- in
+    // signmap (sign_map_words() uint32 per plane, layout in tfft_pencil.cu); spec rows are NOT written.
+    uint32_t* signmap;
+    double sign_alpha;
 };
+// uint32 words per plane of the sign map of a 4096-row plane with `cols` stored columns
+inline size_t sign_map_words(int cols) { return (size_t)(cols / 2) * 16 * 8; }
 // number of samples per plane the 4096-point column pass delivers for a half-spectrum plane of PW columns (0: none)
 inline unsigned col_pass_samples(int PH, int PW_full, int half) { return (PH == 4096 && half) ? (unsigned)(PW_full / 4) * 256u : 0u; }
 
@@ -68,6 +75,7 @@ struct Launcher {
     int fft_impl;  // 0 = v0 (simple shared-memory radix-2), 1 = pencil kernels
 };
 
+bool signmap_supported(const Launcher& L);  // PassArgs::signmap is available (TMA column kernel in use)
 cudaError_t build_twiddles(double2* d_tw, cudaStream_t s);  // fills TW_N/2 entries
 cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a);
 
@@ -111,7 +119,12 @@ cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, Spe
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
                            uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
 
-// window of the workspace a bin list touches: d_out2[0] = 1 + largest stored row, d_out2[1] = 1 + largest stored column
+// the same votes from a sign map (PassArgs::signmap) of planes with `cols` stored columns; bins must not need the mirror
+cudaError_t launch_extract_signmap(const Launcher& L, const uint32_t* signmap, int cols, int nimg, SpecLayout lay,
+                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+
+// window of the workspace a bin list touches: d_out2[0] = 1 + largest stored row, [1] = 1 + largest stored column,
+// [2] = some bin is read through its Hermitian mirror (three unsigned)
 cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t nbins, SpecLayout lay, unsigned* d_out2);
 
 // unfused image <-> plane conversion for sizes the fused row passes do not cover (PW or PH > 4096)

@@ -446,7 +446,30 @@ struct ColTmaArgs {
     unsigned long long* sample_q;
     unsigned sample_stride;   // entries per plane
     int sample_groups;        // column pairs that hold interior columns (PW_full / 4)
+    // pencil_col_tma_w<.., SIGN = true>: no spectrum is stored, only the bit read_bit_from_bin (S:734-746) would read at
+    // every element, packed as signmap[((plane * map_groups + g) * 16 + k1) * 8 + k3] bit (2 m + c) for row
+    // k1 + 16 m + 256 k3 of column 2 g + c
+    uint32_t* signmap;
+    int map_groups;           // column pairs per plane in the map (PW / 2)
+    double alpha;
 };
+
+// read_bit_from_bin (S:734-746) in full: atan2, circular distances to +alpha and -alpha, ties read 1
+__device__ __noinline__ int read_bit_full(double re, double im, double alpha) {
+    const double PI = 3.14159265358979323846;
+    const double th = atan2(im, re);
+    double dp = fmod(th - alpha + PI, 2 * PI);
+    if (dp < 0) dp += 2 * PI;
+    double dn = fmod(th + alpha + PI, 2 * PI);
+    if (dn < 0) dn += 2 * PI;
+    return fabs(dp - PI) <= fabs(dn - PI) ? 1 : 0;
+}
+// For alpha in [1e-6, pi - 1e-6] the two distances differ by 2 min(|th|, alpha, pi - |th|, pi - alpha), so away from
+// the real axis the verdict is simply the sign of the imaginary part; within 1e-9 of it the full formula decides.
+__device__ __forceinline__ int read_bit_sign(double2 z, double alpha) {
+    if (fabs(z.y) > 1e-9 * fabs(z.x)) return z.y > 0.0 ? 1 : 0;
+    return read_bit_full(z.x, z.y, alpha);
+}
 
 template <int S, int LOG2N, int VEC>
 __global__ void __launch_bounds__(512, 1) pencil_col_tma(const __grid_constant__ CUtensorMap in_map,
@@ -539,9 +562,11 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 //      other boxes are neither loaded nor read, and stage 1 folds the zero butterflies away.
 // K3N: only the first K3N 256-row blocks of the output are kept (inverse pass before the crop): the
 //      other results are neither computed (dead code) nor staged.
-template <int S, int NZ, int K3N>
+// SIGN: forward pass of an extract without jitter -- nothing but the read bit of every element is kept (K3N <= 8).
+template <int S, int NZ, int K3N, bool SIGN = false>
 __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant__ CUtensorMap in_map,
                                                            const __grid_constant__ CUtensorMap out_map, ColTmaArgs a) {
+    static_assert(!SIGN || (S > 0 && K3N <= 8), "sign map: forward pass, at most 2048 rows");
     constexpr int LOG2N = 12, VEC = 2;
     using G = Geo<LOG2N, VEC>;
     constexpr int BOX_ROWS = 256, NBOX = G::N / BOX_ROWS;
@@ -596,7 +621,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
         mbar_arrive(&lfree);
-        if (tid == TLAST) {  // its own store of the previous pair's last half has finished reading X
+        if (!SIGN && tid == TLAST) {  // its own store of the previous pair's last half has finished reading X
             tma_wait_read_all();
             mbar_arrive(&xfree_a);
         }
@@ -609,7 +634,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         dft<S, 16>(x);
         twiddle<16>(x, ttw.s2v());
         double2 z[16];
-        mbar_wait(&xfree_a, parity);
+        if constexpr (!SIGN) mbar_wait(&xfree_a, parity);  // (SIGN: X is only ever touched by its own warp)
 #pragma unroll
         for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].x;
         __syncwarp();
@@ -623,6 +648,18 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
         dft<S, 16>(z);  // z[oidx(k3)] = output row k1 + 16*m + 256*k3 of column c
         const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
+        if constexpr (SIGN) {
+            // lane = 2 m + c: one ballot per row block gives the 16 rows x 2 columns of this warp; lane k3 stores word k3
+            unsigned mine = 0;
+#pragma unroll
+            for (int k3 = 0; k3 < K3N; k3++) {
+                const unsigned w = __ballot_sync(0xffffffffu, read_bit_sign(z[oidx<16>(k3)], a.alpha));
+                if ((tid & 31) == k3) mine = w;
+            }
+            if ((tid & 31) < 8) a.signmap[(((size_t)plane * a.map_groups + g) * 16 + k1) * 8 + (tid & 31)] = mine;
+            __syncwarp();  // the next pair's exchange writes come after every lane's reads of the slice
+            continue;
+        }
         // ---- first half of the results: rows with k3 < 8
         __syncwarp();  // every lane is past its reads of the slice
 #pragma unroll
@@ -1328,7 +1365,7 @@ inline int col_groups(const PassArgs& p, int vec) {
     return need < all ? need : all;
 }
 
-template <int S, int NZ, int K3N>
+template <int S, int NZ, int K3N, bool SIGN = false>
 cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     using G = pk::Geo<12, 2>;
     CUtensorMap in_map, out_map;
@@ -1340,8 +1377,9 @@ cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     a.sample_q = S > 0 ? p.sample_q : nullptr;
     a.sample_stride = p.sample_stride;
     a.sample_groups = (int)(p.sample_stride ? (p.PW - 16) / 2 : 0);  // p.PW is ld = PW_full/2 + 16 here: pairs below the Nyquist column
+    a.signmap = SIGN ? p.signmap : nullptr; a.map_groups = p.PW / 2; a.alpha = p.sign_alpha;
     const size_t smem = G::L_BYTES + G::X_BYTES;
-    auto kern = pk::pencil_col_tma_w<S, NZ, K3N>;
+    auto kern = pk::pencil_col_tma_w<S, NZ, K3N, SIGN>;
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, a);
@@ -1359,6 +1397,7 @@ cudaError_t run_col_tma(const Launcher& L, const PassArgs& p, bool* ok) {
     pk::ColTmaArgs a;
     a.tw = p.tw; a.groups_per_plane = col_groups(p, VEC); a.nitems = (long long)p.nplanes * a.groups_per_plane;
     a.sample_q = nullptr; a.sample_stride = 0; a.sample_groups = 0;
+    a.signmap = nullptr; a.map_groups = 0; a.alpha = 0.0;
     const size_t smem = G::L_BYTES + G::X_BYTES;
     auto kern = pk::pencil_col_tma<S, LOG2N, VEC>;
     cudaError_t e = set_smem(kern, smem);
@@ -1446,6 +1485,12 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
                          : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
     if constexpr (LOG2N == 12) {  // warp-local exchange + permuting store (TFFT_COL_KERNEL=block keeps the 9-barrier kernel)
         static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
+        if (p.signmap) {  // extract without jitter: the pass only leaves the read bits behind (the caller checked signmap_supported)
+            if (L.fft_impl != 1 || blockk || p.inverse || p.out_rows > 8 * 256 || p.PW < 2) return cudaErrorNotSupported;
+            bool ok = false;
+            cudaError_t e = p.in_rows <= 9 * 256 ? run_col_tma_w<+1, 9, 8, true>(L, p, &ok) : run_col_tma_w<+1, 16, 8, true>(L, p, &ok);
+            return (e == cudaSuccess && !ok) ? cudaErrorNotSupported : e;
+        }
         if (L.fft_impl != 2 && !blockk && p.PW >= 2) {
             bool ok = false;
             // zero structure of a padded image (UHD: 2160 of 4096 rows): 9 of 16 row blocks carry data
@@ -1468,8 +1513,14 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
 
 }  // namespace
 
+bool signmap_supported(const Launcher& L) {
+    static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
+    return L.fft_impl == 1 && !blockk && get_encoder() != nullptr;
+}
+
 cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* handled) {
     *handled = true;
+    if (p.signmap && !(p.log2n == 12 && p.axis == 1)) return cudaErrorNotSupported;
     // the fused u8 passes need W <= PW == N (always true) and run along x only
     switch (p.log2n) {
         case 12: return dispatch<12>(L, p);

@@ -117,11 +117,13 @@ def test_embed_extract_vs_oracle(ctx, W, H, nbits, center, alpha):
         assert np.array_equal(dec[0], wdec)
 
 
-@pytest.mark.parametrize("W,H", [(600, 4096), (1024, 700), (520, 3000), (300, 200)])
+@pytest.mark.parametrize("W,H", [(600, 4096), (1024, 700), (520, 3000), (300, 200), (64, 4096), (2100, 2500)])
 def test_extract_window_any_bins(ctx, W, H):
     """An extract only transforms the part of the spectrum its bin list reads (rows / columns beyond the last bin are
     neither stored nor transformed).  Bin lists anywhere in the plane -- the annulus corner, the whole plane, right of
-    the Nyquist column (read through the Hermitian mirror), the last rows -- must give the oracle's bits."""
+    the Nyquist column (read through the Hermitian mirror), the last rows -- must give the oracle's bits.  On 4096-row
+    planes the pass leaves only the read bit of every element when the list stays inside the first 2048 stored rows
+    (corner, one_bin, and low_rows / right_half on the full-spectrum layout of the 64-pixel-wide case)."""
     o = oracle()
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
     img = synth.gen_texture(W, H, W + H)
@@ -243,12 +245,63 @@ def test_median_exact_many_planes(ctx):
             assert abs(med[i, p] - want) <= 4e-16 * want, (i, p, med[i, p], want)
 
 
+@pytest.mark.parametrize("W,H,n", [(700, 3000, 3), (4096, 4096, 1), (3840, 2160, 2), (512, 2100, 4)])
+def test_median_4096_rows(ctx, W, H, n):
+    """4096-row half-spectrum planes: the forward column pass drops the median sample while its results are on chip
+    (no gather pass).  Medians must be the exact order statistic of the GPU spectrum, the capacity count the oracle
+    port's (counted on its own spectrum), for every plane of a batch."""
+    imgs = np.stack([synth.gen_texture(W, H, 70 + i) if i % 2 == 0 else synth.gen_cover(W, H, 70 + i) for i in range(n)])
+    _, usable, med = ctx.embed_batch(imgs, np.zeros(0, np.uint32), np.zeros((n, 0), np.uint8))
+    o = O.port()
+    for i in range(n):
+        F = ctx.forward_spectrum(imgs[i])
+        for p in range(3):
+            mags = np.hypot(F[p].real, F[p].imag).ravel()
+            want = np.partition(mags, mags.size // 2)[mags.size // 2]
+            assert abs(med[i, p] - want) <= 4e-16 * want, (i, p, med[i, p], want)
+        if i == 0:
+            Fo = o.forward_spectrum(imgs[i])
+            wus = sum(o.count_plane(Fo[p], 0.05, 0.45, 0.01 * o.median_abs(Fo[p])) for p in range(3))
+            assert int(usable[i]) == wus
+
+
+@pytest.mark.parametrize("kind", ["flat", "half_flat", "two_level"])
+def test_median_fallback_4096_rows(ctx, kind):
+    """The same degenerate planes as test_median_fallback_large_plane on the 4096-row path (the bracket from the column
+    pass's sample cannot isolate the median -> device-side fallback), checked against numpy on the GPU spectrum."""
+    H, W = 4096, 512
+    img = np.full((H, W, 3), 100, np.uint8)
+    if kind == "half_flat":
+        img[:, W // 2:, :] = synth.gen_texture(W // 2, H, 3)
+    elif kind == "two_level":
+        img[::2, :, 1] = 30
+    _, usable, med = ctx.embed_batch(img[None], np.zeros(0, np.uint32), np.zeros((1, 0), np.uint8))
+    F = ctx.forward_spectrum(img)
+    o = O.port()
+    for p in range(3):
+        mags = np.hypot(F[p].real, F[p].imag).ravel()
+        want = np.partition(mags, mags.size // 2)[mags.size // 2]
+        assert abs(med[0, p] - want) <= 4e-16 * want + 1e-7, (p, med[0, p], want)
+    wus = sum(o.count_plane(F[p], 0.05, 0.45, 0.01 * med[0, p]) for p in range(3))
+    assert int(usable[0]) == wus
+
+
 def test_read_ties(ctx):
     """read_bit_from_bin ties -> 1: a flat image has exact zeros in the annulus."""
     cover = np.zeros((32, 32, 3), np.uint8)
     bins = synth.random_bins(32, 32, 60, 1)
     dec, raw = ctx.extract_bits(cover[None], bins, 1)
     assert raw.min() == 1
+
+
+def test_read_ties_sign_map(ctx):
+    """The same ties through the 4096-row column pass that keeps read bits instead of spectra (exact zeros -> 1)."""
+    cover = np.zeros((4096, 64, 3), np.uint8)
+    bins = synth.random_bins(4096, 64, 300, 1)
+    dec, raw = ctx.extract_bits(cover[None], bins, 1)
+    assert raw.min() == 1
+    wdec, wraw = oracle().extract(cover, bins, 1)
+    assert np.array_equal(raw[0], wraw)
 
 
 def test_jitter_hook(ctx):
@@ -279,9 +332,10 @@ def test_empty_inputs(ctx):
         ctx.extract_bits(cover[None], np.zeros(4, np.uint32), 5)  # rep 5 is dead code upstream (S:477)
 
 
-def test_device_pointer_api(ctx):
+@pytest.mark.parametrize("W,H,n", [(320, 200, 3), (600, 4096, 2)])
+def test_device_pointer_api(ctx, W, H, n):
     import torch
-    W, H, n, nbits = 320, 200, 3, 4000
+    nbits = 4000
     PH, PW = synth.next_pow2(H), synth.next_pow2(W)
     covers = np.stack([synth.gen_texture(W, H, 40 + i) for i in range(n)])
     bins = synth.random_bins(PH, PW, nbits, 3)

@@ -57,7 +57,9 @@ def test_pipeline_embed_extract_on_gpu(tmp_path):
         covers.append(p); outs.append(str(tmp_path / f"s{i}.png")); secrets.append(s)
     prm = pipeline.Params(pbkdf2_iter=1000)
     with sb.Context(0) as ctx, pipeline.ImagePipeline(ctx, workers=4, chunk=2) as pl:
-        emb = pl.embed_files(covers, outs, secrets, PASS, prm)
+        # fixed salts: with the reference's random salt (S:927-929) about one 256x256 round trip in 80 loses a header or
+        # payload bit to the channel itself (tools/scan_salts.py), upstream included
+        emb = pl.embed_files(covers, outs, secrets, PASS, prm, salts=[bytes([k] * 16) for k in range(len(covers))])
         assert [r.ok for r in emb] == [True] * 5 + [False]
         assert emb[5].error.startswith("Message too large. Need ")
         ext = pl.extract_files(outs[:5] + [covers[0]], PASS, prm)
