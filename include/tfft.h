@@ -28,7 +28,7 @@
  * TFFT_SPECTRUM=full (no Hermitian halving), TFFT_WIDE=0 (8192-pixel rows and tall images on the
  * unfused four-step path), TFFT_COL_SAMPLE=0 (median sample by a separate gather pass),
  * TFFT_EXTRACT_WINDOW=0 (extract transforms every column and keeps every row), TFFT_SIGNMAP=0 (extract
- * keeps spectra instead of read bits), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
+ * keeps spectra instead of read bits), TFFT_SCAN_Q32=0 (median scan reads the spectrum, not a float copy of |F|^2), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
  * images per chunk, chunks in flight), TFFT_PINGPONG=1, TFFT_ROW_UNITS=1, TFFT_SCAN_CTAS (experiments).
  */
 #ifndef TFFT_H

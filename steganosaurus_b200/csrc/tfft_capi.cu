@@ -25,6 +25,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf spec, spec2, in, out, bits, med, medians, usable, outbytes, raw;  // spec2: scratch of the four-step passes (dims > 4096)
     DevBuf signmap;  // extract without jitter on 4096-row planes: read bits of every element instead of the spectrum
+    DevBuf q32;      // embed on 4096-row half planes: float copy of |F|^2 left by the column pass for the median scan
     // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
     // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
     // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
@@ -52,6 +53,7 @@ struct tfft_ctx {
     bool col_sample = true; // median sample dropped by the forward column pass (TFFT_COL_SAMPLE=0: separate gather kernel)
     bool use_wide = true;   // 8192-pixel rows on the half-spectrum path; TFFT_WIDE=0 keeps them on the unfused four-step path
     bool use_window = true; // extract: the forward column pass keeps only the rows / columns that hold bins (TFFT_EXTRACT_WINDOW=0: all)
+    bool use_q32 = true;     // embed, 4096-row half planes: the median scan reads a float copy of |F|^2 (TFFT_SCAN_Q32=0: the spectrum)
     bool use_signmap = true; // extract without jitter, 4096-row planes: the column pass leaves read bits, not spectra (TFFT_SIGNMAP=0)
     unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
     unsigned* h_win = nullptr;  // ... and read back through this pinned pair
@@ -261,6 +263,7 @@ struct BinWindow { int rows = 0, cols = 0, mirrored = 0; };  // mirrored: some b
 struct FwdOpts {
     unsigned long long* sample_q = nullptr;  // embed, 4096-row half planes: the column pass drops the median sample here
     unsigned sample_stride = 0;
+    float* q32 = nullptr;                    // ... and a float copy of |F|^2 of every element
     const BinWindow* win = nullptr;          // extract: part of the workspace the bin list reads
     uint32_t* signmap = nullptr;             // extract: leave read bits (for this alpha) instead of the column-pass spectrum
     double alpha = 0.0;
@@ -299,7 +302,7 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         if (where) *where = tmp;
         return TFFT_OK;
     }
-    a.sample_q = o.sample_q; a.sample_stride = o.sample_stride;
+    a.sample_q = o.sample_q; a.sample_stride = o.sample_stride; a.q32 = o.q32;
     double out_rows = (double)g.PH, ncols = cols;
     int kind = TFFT_K_COL_FWD;
     if (win && ctx->use_window && win->rows > 0 && win->cols > 0 && (win->rows < g.PH || win->cols < g.ld)) {
@@ -313,6 +316,7 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         a.signmap = o.signmap; a.sign_alpha = o.alpha;
         out_bytes = out_rows * ncols / 8.0;
     }
+    if (o.q32) out_bytes += 4.0 * out_rows * ncols;
     { ProfScope ps(ctx, L.stream, kind, (double)nimg * 3.0 * (16.0 * (double)g.H * ncols + out_bytes)); CK(launch_fft_pass(L, a)); }
     return TFFT_OK;
 }
@@ -360,12 +364,19 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     if (presampled > mw.cand_cap) presampled = 0;
     FwdOpts fo;
     if (presampled) { fo.sample_q = (unsigned long long*)mw.cand; fo.sample_stride = mw.cand_cap; }
+    // ... and a float copy of q = |F|^2 of every element: the scan then reads 4 bytes per element instead of 16
+    const bool q32 = presampled && ctx->use_q32 && signmap_supported(L);
+    if (q32) {
+        int rc2 = ensure(ctx, S.q32, (size_t)nimg * 3 * g.E * sizeof(float));
+        if (rc2) return rc2;
+        fo.q32 = (float*)S.q32.p;
+    }
     int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_cover, nimg, g, center, &spec, fo);
     if (rc) return rc;
     double2* other = spec == (double2*)S.spec.p ? (double2*)S.spec2.p : (double2*)S.spec.p;
     const int m = std::min(g.PH, g.PW);
-    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.E);
-      CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable, presampled)); }
+    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * (q32 ? 4.0 : 16.0) * (double)g.E);
+      CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable, presampled, q32 ? (const float*)S.q32.p : nullptr)); }
     { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
       CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
     return inverse_images(ctx, L, spec, other, d_stego, nimg, g, center);
@@ -525,6 +536,7 @@ int tfft_create(int device, tfft_ctx** out) {
     if (const char* cs = getenv("TFFT_COL_SAMPLE")) ctx->col_sample = atoi(cs) != 0;
     if (const char* ew = getenv("TFFT_EXTRACT_WINDOW")) ctx->use_window = atoi(ew) != 0;
     if (const char* sm = getenv("TFFT_SIGNMAP")) ctx->use_signmap = atoi(sm) != 0;
+    if (const char* sq = getenv("TFFT_SCAN_Q32")) ctx->use_q32 = atoi(sq) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
@@ -543,7 +555,7 @@ void tfft_destroy(tfft_ctx* ctx) {
     for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
         release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.med);
-        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap);
+        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap); release(S.q32);
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }

@@ -713,6 +713,132 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __
         if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
 }
 
+// The same scan over the float copy of q the 4096-row column pass left behind (PassArgs::q32, float4 index
+// ((g * 16 + k1) * 4 + j) * 32 + lane, lane = 2 m + c: rows k1 + 16 m + 256 (4 j + 0..3) of column 2 g + c): 4 bytes per
+// element instead of 16.  A float carries q to 6e-8, so everything outside [qlo (1 - 1e-6), qhi (1 + 1e-6)] is decided
+// on the float alone.  The ~1 % inside (and the rare capacity-relevant magnitudes) are queued per tile and then settled
+// on the exact spectrum values in one dense pass (independent gathers).  Column weights are applied directly (a
+// float4 holds four rows of ONE column), pad columns are skipped.
+constexpr uint32_t Q32_QCAP = 4096;  // queued elements per tile (16 K elements, ~1.3 % expected); overflow -> device fallback flags
+__global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4* __restrict__ q32, const double2* __restrict__ spec, SpecLayout lay,
+                                                                MedianWork w, const Bracket* __restrict__ br, ScanCap cap) {
+    __shared__ uint64_t s_buf[SCAN_SBUF];
+    __shared__ uint32_t s_q[Q32_QCAP];  // element index (24 bits) | float already counted it as below (bit 28) | weight (bits 30..31)
+    __shared__ unsigned s_cnt, s_base, s_nq;
+    __shared__ long long ws[SCAN_THREADS / 32];
+    __shared__ unsigned wc[SCAN_THREADS / 32];
+    const int ip = blockIdx.y;
+    const uint64_t E = lay.plane_elems(), E4 = E / 4;
+    const double2* pl = spec + (size_t)ip * E;
+    const float4* qp = q32 + (size_t)ip * E4;
+    const double qlo = br[ip].qlo, qhi = br[ip].qhi;
+    const double qcap_lo = cap.on ? cap.magmin2 * qlo * (1.0 - 1e-9) : 0.0;
+    const double qcap_hi = cap.on ? cap.magmin2 * qhi * (1.0 + 1e-9) : -1.0;
+    // float thresholds, rounded outwards: below flo -> certainly q < qlo; above fhi -> certainly q > qhi; at most fcap -> look
+    const float flo = __double2float_rd(qlo * (1.0 - 1e-6)), fhi = __double2float_ru(qhi * (1.0 + 1e-6));
+    const float fcap = cap.on ? __double2float_ru(qcap_hi * (1.0 + 1e-6)) : -1.0f;
+    const int hcols = lay.PW >> 1;
+    if (threadIdx.x == 0) s_cnt = 0;
+    long long acc = 0;
+    unsigned capb = 0;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t TILE4 = SCAN_THREADS * SCAN_UNROLL;
+    const uint64_t ntiles = (E4 + TILE4 - 1) / TILE4;
+    const float fnan = __int_as_float(0x7fc00000);
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (threadIdx.x == 0) s_nq = 0;
+        __syncthreads();
+        const uint64_t base = t * TILE4 + threadIdx.x;
+        float4 f[SCAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const uint64_t i4 = base + (uint64_t)u * SCAN_THREADS;
+            f[u] = i4 < E4 ? __ldcs(qp + i4) : make_float4(fnan, fnan, fnan, fnan);
+        }
+        // ---- pass 1: decide on the floats, remember which elements need the exact value (bit 4 u + e)
+        unsigned look = 0, counted = 0;
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const uint64_t i4 = base + (uint64_t)u * SCAN_THREADS;
+            const int x = 2 * (int)(i4 >> 11) + (int)(i4 & 1);
+            const int wgt = (x == 0 || x == hcols) ? 1 : (x < hcols ? 2 : 0);  // Hermitian multiplicity of the column
+            const float qf[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+            unsigned nb = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool b = qf[e] < flo;
+                nb += b ? 1u : 0u;
+                counted |= b ? (1u << (4 * u + e)) : 0u;
+                look |= (wgt != 0 && ((qf[e] >= flo && qf[e] <= fhi) || qf[e] <= fcap)) ? (1u << (4 * u + e)) : 0u;
+            }
+            acc += (long long)(nb * (unsigned)wgt);
+        }
+        // one queue reservation per warp and tile
+        const unsigned cnt = __popc(look);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+        unsigned pos = 0;
+        if (tot) {
+            if (lane == 0) pos = atomicAdd(&s_nq, tot);
+            pos = __shfl_sync(0xffffffffu, pos, 0) + incl - cnt;
+        }
+        while (look) {
+            const int bit = __ffs(look) - 1;
+            look &= look - 1;
+            const uint64_t i4 = base + (uint64_t)(bit >> 2) * SCAN_THREADS;
+            const int ln = (int)(i4 & 31), j = (int)((i4 >> 5) & 3), k1 = (int)((i4 >> 7) & 15), g = (int)(i4 >> 11);
+            const int x = 2 * g + (ln & 1), y = k1 + 16 * (ln >> 1) + 1024 * j + 256 * (bit & 3);
+            const unsigned wgt = (x == 0 || x == hcols) ? 1u : 2u;  // (pad columns never get here)
+            if (pos < Q32_QCAP) s_q[pos] = (unsigned)(y * lay.ld + x) | (((counted >> bit) & 1u) << 28) | (wgt << 30);
+            pos++;
+        }
+        __syncthreads();
+        // ---- pass 2: the queued elements on their exact values
+        const unsigned nq_all = s_nq;
+        const unsigned nq = nq_all < Q32_QCAP ? nq_all : Q32_QCAP;
+        if (nq_all > Q32_QCAP && threadIdx.x == 0) { w.flags[0] = 1; w.flags[1] = 1; }  // hopeless bracket: exact generic passes take over
+        for (unsigned i = threadIdx.x; i - lane < nq; i += SCAN_THREADS) {
+            const bool valid = i < nq;
+            const unsigned ent = valid ? s_q[i] : 0u;
+            const unsigned li = ent & 0xFFFFFFu, wgt = ent >> 30;
+            bool member = false;
+            double2 z = make_double2(0.0, 0.0);
+            if (valid) {
+                z = pl[li];
+                const double q = fma(z.x, z.x, z.y * z.y);
+                const bool lowq = q < qlo;
+                member = !lowq && q <= qhi;
+                if (lowq && !((ent >> 28) & 1u)) acc += wgt;  // (the float alone did not count it)
+                if (q <= qcap_hi) scan_cap_rare(z, q, li, lay, cap, qcap_lo, w, ip, capb);
+                if (member && wgt == 1) {  // staged with the interior weight below: list the excess
+                    const unsigned gb = atomicAdd(&w.cand_b_n[ip], 1u);
+                    if (gb < CAND_B_MAX) w.cand_b[(size_t)ip * CAND_B_MAX + gb] = mag_key(z);
+                }
+            }
+            if (__any_sync(0xffffffffu, member)) scan_stage(member, z, w, ip, s_buf, &s_cnt);
+        }
+        __syncthreads();  // queue and its counter are free for the next tile
+    }
+    for (int o = 16; o; o >>= 1) { acc += __shfl_down_sync(0xffffffffu, acc, o); capb += __shfl_down_sync(0xffffffffu, capb, o); }
+    if (lane == 0) { ws[threadIdx.x >> 5] = acc; wc[threadIdx.x >> 5] = capb; }
+    __syncthreads();
+    const unsigned nloc = s_cnt < SCAN_SBUF ? s_cnt : SCAN_SBUF;
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        unsigned c = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; k++) { t += ws[k]; c += wc[k]; }
+        if (t) atomicAdd((unsigned long long*)&w.counts[ip], (unsigned long long)t);
+        if (c) atomicAdd((unsigned long long*)&w.cap_below[ip], (unsigned long long)c);
+        s_base = nloc ? atomicAdd(&w.cand_n[ip], nloc) : 0;
+    }
+    __syncthreads();
+    uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
+    for (unsigned i = threadIdx.x; i < nloc; i += blockDim.x)
+        if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
+}
+
 // one CTA per plane: exact rank among the members, or raise the fallback flag
 __global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, uint32_t wa, double* median, int* flag, uint32_t guard) {
     __shared__ SelectScratch sc;
@@ -822,7 +948,7 @@ static uint64_t annulus_total_host(int PH, int PW, int ymax, int xmax, double rl
 
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable, unsigned presampled) {
+                                   double* d_median, uint64_t* d_usable, unsigned presampled, const float* q32) {
     const int PH = lay.PH, PW = lay.PW;
     const uint64_t P = (uint64_t)PH * PW;        // size of the full multiset (ranks refer to it)
     const uint64_t E = lay.plane_elems();        // stored elements per plane
@@ -863,7 +989,14 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         unsigned cc = cap_env ? cap_env : (unsigned)((ntiles + 6) / 7);
         if (cc < 1) cc = 1;
         const unsigned per_plane = (unsigned)(ntiles < cc ? ntiles : cc);
-        median_scan<<<dim3(per_plane, (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>(spec, lay, w, br, cap);
+        if (q32 && lay.half && PH == 4096 && !all) {
+            const uint64_t nt4 = (E / 4 + SCAN_TILE - 1) / SCAN_TILE;  // tiles of float4 (four elements each)
+            unsigned c4 = cap_env ? cap_env : (unsigned)((nt4 + 1) / 2);  // ~2 tiles (32 K elements) per CTA, as above
+            if (c4 < 1) c4 = 1;
+            median_scan_q32<<<dim3((unsigned)(nt4 < c4 ? nt4 : c4), (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>((const float4*)q32, spec, lay, w, br, cap);
+        } else {
+            median_scan<<<dim3(per_plane, (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>(spec, lay, w, br, cap);
+        }
         TFFT_LAUNCH_CHECK(L);
     }
     median_members<<<nplanes, 1024, 0, L.stream>>>(w, P, lay.half ? 2u : 1u, d_median, d_flag, all ? 0u : RANK_GUARD);

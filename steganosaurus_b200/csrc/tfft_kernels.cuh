@@ -48,6 +48,10 @@ struct PassArgs {
     // median bracket is then built from it without a separate gather pass over the spectrum.
     unsigned long long* sample_q;
     unsigned sample_stride;
+    // ... and (optional, with sample_q) q of EVERY element as a float, q32[plane * PH * PW + ...] in the kernel's own
+    // warp order (float4 [g][k1][j][lane], tfft_pencil.cu): the median scan then reads 4 bytes per element instead of 16
+    // and goes back to the spectrum only for the ~1 % of elements whose float cannot decide (median_scan_q32).
+    float* q32;
     // Forward 4096-point column pass of an extract without jitter (optional, out_rows <= 2048): instead of the spectrum
     // the pass leaves one bit per element -- what read_bit_from_bin (S:734-746) reads there with this alpha -- in
     // signmap (sign_map_words() uint32 per plane, layout in tfft_pencil.cu); spec rows are NOT written.
@@ -105,9 +109,10 @@ size_t median_work_bytes(int nplanes, uint32_t cand_cap);
 void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap);
 // d_median: [nplanes]; d_usable: [nplanes/3] (sum over the 3 planes of count/2)
 // presampled > 0: w.cand already holds that many q-keys per plane (written by the column pass), no gather pass
+// q32 != null (4096-row half planes): float copy of q = |F|^2 of every element left by the column pass (PassArgs::q32)
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable, unsigned presampled = 0);
+                                   double* d_median, uint64_t* d_usable, unsigned presampled = 0, const float* q32 = nullptr);
 
 // ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
 cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,

@@ -446,6 +446,9 @@ struct ColTmaArgs {
     unsigned long long* sample_q;
     unsigned sample_stride;   // entries per plane
     int sample_groups;        // column pairs that hold interior columns (PW_full / 4)
+    // with sample_q (optional): q of every element as a float; as float4 [plane][g][k1][j][lane = 2 m + c] holding rows
+    // k1 + 16 m + 256 (4 j + 0..3) of column 2 g + c: four fully coalesced 512-byte warp stores per pair
+    float* q32;
     // pencil_col_tma_w<.., SIGN = true>: no spectrum is stored, only the bit read_bit_from_bin (S:734-746) would read at
     // every element, packed as signmap[((plane * map_groups + g) * 16 + k1) * 8 + k3] bit (2 m + c) for row
     // k1 + 16 m + 256 k3 of column 2 g + c
@@ -659,6 +662,21 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
             if ((tid & 31) < 8) a.signmap[(((size_t)plane * a.map_groups + g) * 16 + k1) * 8 + (tid & 31)] = mine;
             __syncwarp();  // the next pair's exchange writes come after every lane's reads of the slice
             continue;
+        }
+        if constexpr (S > 0 && K3N == 16) {
+            if (a.q32 != nullptr) {  // (uniform) float copy of q = |F|^2 for the median scan
+                float4* dst = (float4*)a.q32 + (((size_t)plane * a.map_groups + g) * 16 + k1) * 128 + (tid & 31);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float f[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double2 v = z[oidx<16>(4 * j + u)];
+                        f[u] = __double2float_rn(fma(v.x, v.x, v.y * v.y));
+                    }
+                    dst[j * 32] = make_float4(f[0], f[1], f[2], f[3]);
+                }
+            }
         }
         // ---- first half of the results: rows with k3 < 8
         __syncwarp();  // every lane is past its reads of the slice
@@ -1378,6 +1396,7 @@ cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     a.sample_stride = p.sample_stride;
     a.sample_groups = (int)(p.sample_stride ? (p.PW - 16) / 2 : 0);  // p.PW is ld = PW_full/2 + 16 here: pairs below the Nyquist column
     a.signmap = SIGN ? p.signmap : nullptr; a.map_groups = p.PW / 2; a.alpha = p.sign_alpha;
+    a.q32 = (S > 0 && K3N == 16 && !SIGN && p.col_limit == 0) ? p.q32 : nullptr;
     const size_t smem = G::L_BYTES + G::X_BYTES;
     auto kern = pk::pencil_col_tma_w<S, NZ, K3N, SIGN>;
     cudaError_t e = set_smem(kern, smem);
@@ -1397,7 +1416,7 @@ cudaError_t run_col_tma(const Launcher& L, const PassArgs& p, bool* ok) {
     pk::ColTmaArgs a;
     a.tw = p.tw; a.groups_per_plane = col_groups(p, VEC); a.nitems = (long long)p.nplanes * a.groups_per_plane;
     a.sample_q = nullptr; a.sample_stride = 0; a.sample_groups = 0;
-    a.signmap = nullptr; a.map_groups = 0; a.alpha = 0.0;
+    a.signmap = nullptr; a.map_groups = 0; a.alpha = 0.0; a.q32 = nullptr;
     const size_t smem = G::L_BYTES + G::X_BYTES;
     auto kern = pk::pencil_col_tma<S, LOG2N, VEC>;
     cudaError_t e = set_smem(kern, smem);
