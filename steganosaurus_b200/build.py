@@ -25,7 +25,7 @@ CLI = os.path.join(PKG, "turtlefft")
 NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-march=x86-64-v3", "-Xcompiler", "-ffp-contract=off", "--expt-relaxed-constexpr",
 ]
 CXX = shutil.which("g++") or "g++"
 CXX_FLAGS = ["-std=c++17", "-O3", "-march=x86-64-v3", "-fPIC", "-Wall", "-Wextra"]

@@ -457,18 +457,28 @@ bool bins_ok(const uint32_t* bins, size_t n, size_t P) {
 }
 // the same check plus the window of the workspace the list touches (same rule as the bins_window kernel)
 bool bins_ok_window(const uint32_t* bins, size_t n, const Geom& g, BinWindow& w) {
-    uint32_t bad = 0;
-    int ry = 0, rx = 0;
-    const uint32_t P = (uint32_t)std::min<size_t>(g.P, 0x40000000u);
-    for (size_t i = 0; i < n; i++) {
+    uint32_t bad = 0, ry = 0, rx = 0;
+    const uint32_t P = (uint32_t)std::min<size_t>(g.P, 0x40000000u), xmask = (uint32_t)(g.PW - 1);
+    const int lw = g.lw;
+    for (size_t i = 0; i < n; i++) {  // branch-free: largest row and column as listed
         const uint32_t lin = bins[i] & 0x3FFFFFFFu;
         bad |= (uint32_t)((bins[i] >> 30) > 2) | (uint32_t)(lin >= P);
-        int y = (int)(lin >> g.lw), x = (int)(lin & (uint32_t)(g.PW - 1));
-        if (g.half && x > (g.PW >> 1)) { y = (g.PH - y) & (g.PH - 1); x = g.PW - x; w.mirrored = 1; }
-        ry = std::max(ry, y + 1);
-        rx = std::max(rx, x + 1);
+        ry = std::max(ry, lin >> lw);
+        rx = std::max(rx, lin & xmask);
     }
-    w.rows = ry; w.cols = rx;
+    w.rows = (int)ry + 1; w.cols = (int)rx + 1; w.mirrored = 0;
+    if (n == 0) { w.rows = 0; w.cols = 0; }
+    if (g.half && (int)rx > (g.PW >> 1) && !bad) {  // some bin sits behind the Nyquist column: redo with the mirror rule
+        int my = 0, mx = 0;
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t lin = bins[i] & 0x3FFFFFFFu;
+            int y = (int)(lin >> lw), x = (int)(lin & xmask);
+            if (x > (g.PW >> 1)) { y = (g.PH - y) & (g.PH - 1); x = g.PW - x; }
+            my = std::max(my, y + 1);
+            mx = std::max(mx, x + 1);
+        }
+        w.rows = my; w.cols = mx; w.mirrored = 1;
+    }
     return !bad;
 }
 // device bin list: reduce on the device, read the two numbers back (one stream synchronisation per call)

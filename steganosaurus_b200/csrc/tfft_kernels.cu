@@ -716,15 +716,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan(const double2* __
 // The same scan over the float copy of q the 4096-row column pass left behind (PassArgs::q32, float4 index
 // ((g * 16 + k1) * 4 + j) * 32 + lane, lane = 2 m + c: rows k1 + 16 m + 256 (4 j + 0..3) of column 2 g + c): 4 bytes per
 // element instead of 16.  A float carries q to 6e-8, so everything outside [qlo (1 - 1e-6), qhi (1 + 1e-6)] is decided
-// on the float alone.  The ~1 % inside (and the rare capacity-relevant magnitudes) are queued per tile and then settled
-// on the exact spectrum values in one dense pass (independent gathers).  Column weights are applied directly (a
+// on the float alone.  The ~1 % inside (and the rare capacity-relevant magnitudes) are queued per warp and tile and then
+// settled on the exact spectrum values in one dense pass (independent gathers, no block barrier in the loop).  Column weights are applied directly (a
 // float4 holds four rows of ONE column), pad columns are skipped.
-constexpr uint32_t Q32_QCAP = 4096;  // queued elements per tile (16 K elements, ~1.3 % expected); overflow -> device fallback flags
+constexpr uint32_t Q32_WQ = 256;  // queued elements per warp and tile (1024 elements, ~13 expected); overflow -> device fallback flags
 __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4* __restrict__ q32, const double2* __restrict__ spec, SpecLayout lay,
                                                                 MedianWork w, const Bracket* __restrict__ br, ScanCap cap) {
     __shared__ uint64_t s_buf[SCAN_SBUF];
-    __shared__ uint32_t s_q[Q32_QCAP];  // element index (24 bits) | float already counted it as below (bit 28) | weight (bits 30..31)
-    __shared__ unsigned s_cnt, s_base, s_nq;
+    // per-warp queues (no block barrier inside the tile loop):
+    // element index (24 bits) | float already counted it as below (bit 28) | weight (bits 30..31)
+    __shared__ uint32_t s_q[SCAN_THREADS / 32][Q32_WQ];
+    __shared__ unsigned s_cnt, s_base;
     __shared__ long long ws[SCAN_THREADS / 32];
     __shared__ unsigned wc[SCAN_THREADS / 32];
     const int ip = blockIdx.y;
@@ -739,15 +741,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4*
     const float fcap = cap.on ? __double2float_ru(qcap_hi * (1.0 + 1e-6)) : -1.0f;
     const int hcols = lay.PW >> 1;
     if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     long long acc = 0;
     unsigned capb = 0;
     const int lane = threadIdx.x & 31;
+    uint32_t* myq = s_q[threadIdx.x >> 5];
     constexpr uint32_t TILE4 = SCAN_THREADS * SCAN_UNROLL;
     const uint64_t ntiles = (E4 + TILE4 - 1) / TILE4;
     const float fnan = __int_as_float(0x7fc00000);
     for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        if (threadIdx.x == 0) s_nq = 0;
-        __syncthreads();
         const uint64_t base = t * TILE4 + threadIdx.x;
         float4 f[SCAN_UNROLL];
 #pragma unroll
@@ -773,17 +775,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4*
             }
             acc += (long long)(nb * (unsigned)wgt);
         }
-        // one queue reservation per warp and tile
+        // the warp's queue: exclusive positions by a prefix sum over the lanes
         const unsigned cnt = __popc(look);
         unsigned incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
-        unsigned pos = 0;
-        if (tot) {
-            if (lane == 0) pos = atomicAdd(&s_nq, tot);
-            pos = __shfl_sync(0xffffffffu, pos, 0) + incl - cnt;
-        }
+        const unsigned nq_all = __shfl_sync(0xffffffffu, incl, 31);
+        if (nq_all == 0) continue;  // (warp-uniform)
+        unsigned pos = incl - cnt;
         while (look) {
             const int bit = __ffs(look) - 1;
             look &= look - 1;
@@ -791,17 +790,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4*
             const int ln = (int)(i4 & 31), j = (int)((i4 >> 5) & 3), k1 = (int)((i4 >> 7) & 15), g = (int)(i4 >> 11);
             const int x = 2 * g + (ln & 1), y = k1 + 16 * (ln >> 1) + 1024 * j + 256 * (bit & 3);
             const unsigned wgt = (x == 0 || x == hcols) ? 1u : 2u;  // (pad columns never get here)
-            if (pos < Q32_QCAP) s_q[pos] = (unsigned)(y * lay.ld + x) | (((counted >> bit) & 1u) << 28) | (wgt << 30);
+            if (pos < Q32_WQ) myq[pos] = (unsigned)(y * lay.ld + x) | (((counted >> bit) & 1u) << 28) | (wgt << 30);
             pos++;
         }
-        __syncthreads();
+        __syncwarp();
         // ---- pass 2: the queued elements on their exact values
-        const unsigned nq_all = s_nq;
-        const unsigned nq = nq_all < Q32_QCAP ? nq_all : Q32_QCAP;
-        if (nq_all > Q32_QCAP && threadIdx.x == 0) { w.flags[0] = 1; w.flags[1] = 1; }  // hopeless bracket: exact generic passes take over
-        for (unsigned i = threadIdx.x; i - lane < nq; i += SCAN_THREADS) {
+        const unsigned nq = nq_all < Q32_WQ ? nq_all : Q32_WQ;
+        if (nq_all > Q32_WQ && lane == 0) { w.flags[0] = 1; w.flags[1] = 1; }  // hopeless bracket: the exact generic passes take over
+        for (unsigned i = lane; i - lane < nq; i += 32) {
             const bool valid = i < nq;
-            const unsigned ent = valid ? s_q[i] : 0u;
+            const unsigned ent = valid ? myq[i] : 0u;
             const unsigned li = ent & 0xFFFFFFu, wgt = ent >> 30;
             bool member = false;
             double2 z = make_double2(0.0, 0.0);
@@ -819,7 +817,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4*
             }
             if (__any_sync(0xffffffffu, member)) scan_stage(member, z, w, ip, s_buf, &s_cnt);
         }
-        __syncthreads();  // queue and its counter are free for the next tile
+        __syncwarp();  // the queue is free for the next tile
     }
     for (int o = 16; o; o >>= 1) { acc += __shfl_down_sync(0xffffffffu, acc, o); capb += __shfl_down_sync(0xffffffffu, capb, o); }
     if (lane == 0) { ws[threadIdx.x >> 5] = acc; wc[threadIdx.x >> 5] = capb; }
