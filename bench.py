@@ -353,8 +353,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "dominant_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            if tj.get("kernel") == name and groups:
+            tj = json.load(open(tpath)).get("kernels", {}).get(name)
+            if tj and groups:
                 # ncu-measured DRAM bytes per image x images in one launch group of this run
                 traffic = tj["dram_bytes_per_image"] * (nbytes / groups) / tj["algorithmic_bytes_per_image"]
         except Exception:
