@@ -149,6 +149,13 @@ int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec_c64, int n, int
                              uint64_t* d_usable, void* stream);
 
 
+/* Host-only (no GPU, no context): the part of the stored spectrum a bin list reads, as the extract entry points
+ * compute it before sizing their forward column pass.  half = 1: half-spectrum workspace (columns 0..PW/2; a bin
+ * right of the Nyquist column is read through its Hermitian mirror ((PH-y)%PH, PW-x), S:370-372), half = 0: full.
+ * rows / cols = 1 + largest stored row / column, mirrored = some bin needs the mirror.  TFFT_E_INVALID for a
+ * plane index above 2 or a bin outside the PH x PW plane. */
+int tfft_bin_window(const uint32_t* bins, size_t nbins, int W, int H, int half, int* rows, int* cols, int* mirrored);
+
 /* ---- per-kernel timing (CUDA events on the launching stream) -------------------------------
  * When enabled, every kernel group the library launches is bracketed by a pair of events; after
  * the caller has synchronised, tfft_profile_read() returns launches and summed device time per

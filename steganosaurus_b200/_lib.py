@@ -18,7 +18,7 @@ SYMBOLS = [
     "tfft_embed_batch", "tfft_embed_batch_dev", "tfft_extract_bits", "tfft_extract_bits_dev",
     "tfft_forward_batch", "tfft_read_bits", "tfft_forward_spectrum", "tfft_fft2d", "tfft_fft2d_dev",
     "tfft_fft_pass_dev", "tfft_median_capacity_dev", "tfft_extract_frame", "tfft_extract_frame_dev",
-    "tfft_profile_enable", "tfft_profile_reset", "tfft_profile_read", "tfft_kind_name",
+    "tfft_profile_enable", "tfft_profile_reset", "tfft_profile_read", "tfft_kind_name", "tfft_bin_window",
 ]
 
 _lib = None
@@ -92,5 +92,7 @@ def load() -> C.CDLL:
     L.tfft_fft_pass_dev.restype = i
     L.tfft_median_capacity_dev.argtypes = [vp, vp, i, i, i, d, d, d, vp, vp, vp]
     L.tfft_median_capacity_dev.restype = i
+    L.tfft_bin_window.argtypes = [vp, sz, i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.tfft_bin_window.restype = i
     _lib = L
     return L

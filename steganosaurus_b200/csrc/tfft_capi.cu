@@ -955,6 +955,20 @@ int tfft_fft2d(tfft_ctx* ctx, double* data, int n, int PH, int PW, int inverse) 
     return TFFT_OK;
 }
 
+int tfft_bin_window(const uint32_t* bins, size_t nbins, int W, int H, int half, int* rows, int* cols, int* mirrored) {
+    if ((nbins && !bins) || W <= 0 || H <= 0) return TFFT_E_INVALID;
+    Geom g;
+    int rc = make_geom(nullptr, W, H, g);  // (no context: full layout) -- only the padded sizes are needed here
+    if (rc) return rc;
+    g.half = half ? 1 : 0;
+    BinWindow w;
+    if (!bins_ok_window(bins, nbins, g, w)) return TFFT_E_INVALID;
+    if (rows) *rows = w.rows;
+    if (cols) *cols = w.cols;
+    if (mirrored) *mirrored = w.mirrored;
+    return TFFT_OK;
+}
+
 int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec, int n, int PH, int PW, double magmin,
                              double rmin, double rmax, double* d_median, uint64_t* d_usable, void* stream) {
     if (!ctx || !d_spec || n <= 0 || !d_median) return TFFT_E_INVALID;

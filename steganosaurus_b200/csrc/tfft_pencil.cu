@@ -15,7 +15,9 @@
 // Kernels:
 //   pencil_u8_fwd_r2c / pencil_u8_inv_c2r   fused u8 RGB <-> half-spectrum rows; two image rows share one complex
 //                                           transform, or (WIDE) one 8192-pixel row is packed into one
-//   pencil_col_tma_w                        4096-point column pairs on the TMA engine, mbarrier hand-offs, zero-block skipping
+//   pencil_col_tma_w                        4096-point column pairs on the TMA engine, mbarrier hand-offs, zero-block skipping;
+//                                           embed forward: also the median sample and a float copy of |F|^2; extract
+//                                           forward (SIGN): no spectrum, one read bit per element
 //   pencil_col_tma, pencil_c2c, pencil_u8_fwd/inv   other sizes / full-spectrum variants / LSU fallback
 //
 // A "unit" is the set of threads that owns one buffer set and works through its own stream of pencils (persistent,
