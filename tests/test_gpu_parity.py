@@ -393,16 +393,25 @@ def test_full_size_roundtrip_properties(ctx):
 
 def test_uhd_matches_reference_failure_mode(ctx):
     """3840x2160 pads to 4096^2 and the crop destroys the signal: the REFERENCE's own extract fails
-    (SURVEY fact 3).  Parity here = same stego pixels / raw bits as the oracle on a small analogue,
-    and a high raw BER on the full UHD size just like upstream."""
+    (SURVEY fact 3).  Parity here = a high raw BER on the full UHD size just like upstream, and the oracle's stego
+    pixels / capacity / medians / raw bits on that very image (about 10 s of reference CPU time)."""
     W, H = 3840, 2160
     nbits = 60000
     cover = synth.gen_cover(W, H, 1001)
     bins = synth.random_bins(4096, 4096, nbits, 5)
     bits = synth.random_bits(1, nbits, 6)
-    stego, usable, _ = ctx.embed_batch(cover[None], bins, bits)
+    stego, usable, med = ctx.embed_batch(cover[None], bins, bits)
     _, raw = ctx.extract_bits(stego, bins, 1)
     assert (raw[0] != bits[0]).mean() > 0.05
+    # ... and at this full BASELINE size the same numbers as the oracle: stego pixels, capacity, medians, raw bits
+    o = oracle()
+    want = o.embed(cover, bins, bits[0])
+    assert int(usable[0]) == want["usable"]
+    assert np.allclose(med[0], want["medians"], rtol=1e-11)
+    assert_pixels(stego[0], want["stego"])
+    _, wraw = o.extract(want["stego"], bins, 1)
+    _, raw2 = ctx.extract_bits(want["stego"][None], bins, 1)
+    assert np.array_equal(raw2[0], wraw)
 
 
 def test_wide_half_path_matches_unfused_path():
