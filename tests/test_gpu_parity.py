@@ -165,6 +165,25 @@ def test_batch_chunking_and_independence(ctx):
         assert np.array_equal(raw[i], wraw) and np.array_equal(dec[i], wdec)
 
 
+def test_batch_4096_rows_vs_oracle(ctx):
+    """Several images through the 4096-row kernels in one call (per-plane offsets of the float copy of |F|^2, the
+    median work lists and the sign map): every image against the oracle on its own."""
+    W, H, n, nbits = 600, 4096, 3, 4998
+    covers = np.stack([synth.gen_texture(W, H, 300 + i) if i != 1 else synth.gen_cover(W, H, 301) for i in range(n)])
+    bins = synth.random_bins(4096, 1024, nbits, 9)
+    bits = synth.random_bits(n, nbits, 10)
+    stego, usable, med = ctx.embed_batch(covers, bins, bits)
+    dec, raw = ctx.extract_bits(stego, bins, 7)
+    o = oracle()
+    for i in range(n):
+        want = o.embed(covers[i], bins, bits[i])
+        assert_pixels(stego[i], want["stego"])
+        assert int(usable[i]) == want["usable"]
+        assert np.allclose(med[i], want["medians"], rtol=1e-11)
+        wdec, wraw = o.extract(stego[i], bins, 7)
+        assert np.array_equal(raw[i], wraw) and np.array_equal(dec[i], wdec)
+
+
 def test_two_phase_extract(ctx):
     g = load_golden("g512_walk")
     ctx.forward_batch(g["stego"][None], g["center"])
