@@ -58,11 +58,24 @@ int tfft_host_parse_header(const uint8_t hdr[38], uint32_t* clen_out, uint8_t sa
 int tfft_host_open_payload(const uint8_t* pass, size_t plen, uint32_t iters, const uint8_t hdr[38],
                            uint8_t* payload, uint32_t clen);
 
+/* ---- --key path (S:576-591, S:603-662, S:1020-1040): a raw 32-byte master key instead of a passphrase ------------
+ * path keys: tfft_host_turtle_keys(master_key, 32, ...) (path_key = SHA256(master_key), S:1036);
+ * AEAD keys: HKDF-Extract(salt, master_key) -> HKDF-Expand("fft_turtle:keys"), no PBKDF2. */
+void tfft_host_derive_keys_raw(const uint8_t master_key[32], const uint8_t salt[16], uint8_t aead_key[32], uint8_t nonce[12]);
+size_t tfft_host_frame_bits_key(const uint8_t master_key[32], const uint8_t salt[16], const uint8_t* secret, size_t slen,
+                                uint8_t* bits_out, uint8_t header_out[38]);
+int tfft_host_open_payload_key(const uint8_t master_key[32], const uint8_t hdr[38], uint8_t* payload, uint32_t clen);
+/* decode_or_unwrap_key: base64 of the raw key, or of the passphrase-wrapped 80-byte form ("TFKW", needs wrap_pass).
+ * 1 ok, 0 undecodable / wrong passphrase, -1 wrapped key without a passphrase. */
+int tfft_host_key_decode(const char* key_b64, const char* wrap_pass, uint32_t iters, uint8_t key_out[32]);
+
 /* ---- PNG (replaces stbi_load(...,3) S:909 / stbi_write_png S:1104) ------------------------- */
-/* Decodes any non-interlaced or Adam7 8/16-bit PNG to 8-bit RGB. Caller frees with tfft_host_free. */
+/* Decodes any non-interlaced or Adam7 8/16-bit PNG to 8-bit RGB (malloc'd; NULL on any failure, including
+ * a dimension above 16384 = TFFT_MAX_DIM).  The caller frees it with tfft_hostlib_free -- NOT with
+ * tfft_host_free of include/tfft.h, which releases pinned CUDA memory (the two libraries share no symbol). */
 uint8_t* tfft_host_png_load(const char* path, int* W, int* H);
 int tfft_host_png_save(const char* path, const uint8_t* rgb, int W, int H);
-void tfft_host_free(void* p);
+void tfft_hostlib_free(void* p);
 
 #ifdef __cplusplus
 }

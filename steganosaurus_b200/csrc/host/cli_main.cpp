@@ -1,8 +1,9 @@
 // cli_main.cpp -- `turtlefft embed|extract`: drop-in for the reference CLI (S:813-877, S:907-1312)
 // on top of the B200 hot path.  Same sub-commands, flags, defaults (Params S:375-381), messages and
 // exit codes for the --pass path; the spectral work is two calls into libtfft_b200.so.
-// Not carried over (out of scope): gen-key / --key / --wrap-pass key management and the
-// experimental --adaptive_alpha / --cover_dependent_path (upstream documents both as broken).
+// --key / --wrap-pass (a raw or passphrase-wrapped 32-byte master key, S:576-662, S:1020-1040) are supported;
+// not carried over (out of scope): gen-key and the experimental --adaptive_alpha /
+// --cover_dependent_path (upstream documents both as broken).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -16,21 +17,20 @@
 namespace {
 
 struct Args {
-    std::string mode, in, out, secret, pass, key;
+    std::string mode, in, out, secret, pass, key, wrap_pass;
     double alpha = 0.50, rmin = 0.05, rmax = 0.45, magmin = 0.01, density = 0.7, jitter = 0.0;  // S:375-381
     bool center = false, adaptive = false, cover_dep = false;
     uint32_t iters = 600000;
-    std::string salt_hex;  // test hook: fixed salt instead of the OS RNG
 };
 
 void usage() {
     fprintf(stderr,
             "Usage:\n"
-            "  turtlefft embed   --in cover.png --out stego.png --secret TEXT --pass PW\n"
+            "  turtlefft embed   --in cover.png --out stego.png --secret TEXT (--pass PW | --key BASE64 [--wrap-pass PW])\n"
             "            [--alpha 0.5 --jitter 0 --density 0.7 --rmin 0.05 --rmax 0.45 --magmin 0.01 --center 0]\n"
             "            [--pbkdf2_iter 600000]\n"
-            "  turtlefft extract --in stego.png --pass PW [same options as embed]\n"
-            "  (B200 build: spectral path on the GPU; gen-key/--key and the experimental\n"
+            "  turtlefft extract --in stego.png (--pass PW | --key BASE64 [--wrap-pass PW]) [same options as embed]\n"
+            "  (B200 build: spectral path on the GPU; gen-key and the experimental\n"
             "   --adaptive_alpha / --cover_dependent_path switches are not part of this build)\n");
 }
 
@@ -47,7 +47,8 @@ bool parse(int argc, char** argv, Args& A) {
             else if (k == "--secret") A.secret = need();
             else if (k == "--pass") A.pass = need();
             else if (k == "--key") A.key = need();
-            else if (k == "--key-out" || k == "--wrap-pass") need();
+            else if (k == "--key-out") need();
+            else if (k == "--wrap-pass") A.wrap_pass = need();
             else if (k == "--alpha") A.alpha = std::stod(need());
             else if (k == "--jitter") A.jitter = std::stod(need());
             else if (k == "--density") A.density = std::stod(need());
@@ -58,7 +59,6 @@ bool parse(int argc, char** argv, Args& A) {
             else if (k == "--pbkdf2_iter") A.iters = (uint32_t)std::stoul(need());
             else if (k == "--adaptive_alpha") A.adaptive = truthy(need());
             else if (k == "--cover_dependent_path") A.cover_dep = truthy(need());
-            else if (k == "--salt-hex") A.salt_hex = need();
             else { fprintf(stderr, "Unknown arg: %s\n", k.c_str()); return false; }  // S:867
         } catch (...) { return false; }
     }
@@ -84,14 +84,27 @@ tfft_ctx* open_ctx() {
     exit(1);
 }
 
-void random_salt(const Args& A, uint8_t salt[16]) {
-    if (A.salt_hex.size() == 32) {
-        for (int i = 0; i < 16; i++) salt[i] = (uint8_t)strtoul(A.salt_hex.substr(2 * i, 2).c_str(), nullptr, 16);
+void random_salt(uint8_t salt[16]) {
+    // TFFT_TEST_SALT_HEX (32 hex digits): the test-suite pins the salt to compare stego pixels with the oracle.  Never set
+    // it otherwise: a repeated salt repeats the AEAD key and nonce for the same passphrase.
+    const char* hex = getenv("TFFT_TEST_SALT_HEX");
+    if (hex && strlen(hex) == 32) {
+        const std::string h(hex);
+        for (int i = 0; i < 16; i++) salt[i] = (uint8_t)strtoul(h.substr(2 * i, 2).c_str(), nullptr, 16);
         return;
     }
     FILE* f = fopen("/dev/urandom", "rb");  // std::random_device upstream (S:927-929)
     if (!f || fread(salt, 1, 16, f) != 16) { fprintf(stderr, "turtlefft: no entropy source\n"); exit(1); }
     fclose(f);
+}
+
+// --key: decode_or_unwrap_key (S:603-662); false when the passphrase path is in use
+bool load_key(const Args& A, uint8_t master[32]) {
+    if (A.key.empty()) return false;
+    const int rc = tfft_host_key_decode(A.key.c_str(), A.wrap_pass.c_str(), A.iters, master);
+    if (rc < 0) fprintf(stderr, "Key is wrapped but no unwrap passphrase provided\n");
+    if (rc != 1) { fprintf(stderr, "Failed to decode/unwrap key from --key argument\n"); exit(1); }  // S:936, S:1149
+    return true;
 }
 
 void do_embed(const Args& A) {
@@ -100,14 +113,20 @@ void do_embed(const Args& A) {
     if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:910
     const int PW = next_pow2(W), PH = next_pow2(H);
     uint8_t salt[16];
-    random_salt(A, salt);
+    random_salt(salt);
     const size_t nbits = 912 + 56 * (A.secret.size() + 16);
     std::vector<uint8_t> bits(nbits);
     uint8_t hdr[38];
-    tfft_host_frame_bits((const uint8_t*)A.pass.data(), A.pass.size(), salt, A.iters, (const uint8_t*)A.secret.data(), A.secret.size(),
-                         bits.data(), hdr);
-    uint8_t path_key[32], sub[128];
-    tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
+    uint8_t path_key[32], sub[128], master[32];
+    if (load_key(A, master)) {  // S:933-939, S:1036
+        tfft_host_frame_bits_key(master, salt, (const uint8_t*)A.secret.data(), A.secret.size(), bits.data(), hdr);
+        tfft_host_turtle_keys(master, 32, path_key, sub);
+        memset(master, 0, sizeof(master));
+    } else {
+        tfft_host_frame_bits((const uint8_t*)A.pass.data(), A.pass.size(), salt, A.iters, (const uint8_t*)A.secret.data(), A.secret.size(),
+                             bits.data(), hdr);
+        tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
+    }
     std::vector<uint32_t> bins(nbits);
     const int wrc = tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, nbits, bins.data(), nullptr, nullptr, 0);
     std::vector<double> jit;
@@ -128,7 +147,7 @@ void do_embed(const Args& A) {
     if (!tfft_host_png_save(A.out.c_str(), out.data(), W, H)) { fprintf(stderr, "PNG write failed: %s\n", A.out.c_str()); exit(1); }  // S:1105
     fprintf(stdout, "Embedded %zu bits into %s (payload %u bytes, ver=2, salt/nonce in header)\n", nbits, A.out.c_str(),
             (unsigned)A.secret.size());  // S:1107
-    tfft_host_free(img);
+    tfft_hostlib_free(img);
     tfft_destroy(ctx);
 }
 
@@ -137,8 +156,10 @@ void do_extract(const Args& A) {
     uint8_t* img = tfft_host_png_load(A.in.c_str(), &W, &H);
     if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:1115
     const int PW = next_pow2(W), PH = next_pow2(H);
-    uint8_t path_key[32], sub[128];
-    tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
+    uint8_t path_key[32], sub[128], master[32];
+    const bool raw_key = load_key(A, master);
+    if (raw_key) tfft_host_turtle_keys(master, 32, path_key, sub);
+    else tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
     tfft_ctx* ctx = open_ctx();
     int rc = tfft_forward_batch(ctx, img, 1, W, H, A.center ? 1 : 0);
     if (rc) die_tfft(ctx, rc);
@@ -155,21 +176,27 @@ void do_extract(const Args& A) {
     if (hrc == 1) { fprintf(stderr, "Magic not found.\n"); exit(1); }                         // S:1237
     if (hrc == 2) { fprintf(stderr, "Unsupported version (%u).\n", hdr[4]); exit(1); }         // S:1238
     const size_t nb = 912 + 56 * ((size_t)clen + 16);
+    // a (noise- or attacker-controlled) length beyond what the annulus can hold cannot be a frame: fail like a walk that
+    // ran out of bins instead of allocating for it (the reference walks forever here)
+    if (nb > (size_t)3 * PH * PW / 2) { fprintf(stderr, "Payload truncated after ECC decode.\n"); exit(1); }
     bins.resize(nb);
     // the same walk continued (S:1260-1264); bounded, unlike upstream
     if (tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, nb, bins.data(), nullptr, nullptr, 0)) {
         fprintf(stderr, "Payload truncated after ECC decode.\n"); exit(1);  // S:1269
     }
     if (A.jitter != 0.0) { jit.resize(nb); tfft_host_jitter(sub, bins.data(), nb, A.jitter, jit.data()); }
-    std::vector<uint8_t> rest(clen + 16);
+    std::vector<uint8_t> rest((size_t)clen + 16);
     if ((rc = tfft_read_bits(ctx, bins.data() + 912, nb - 912, 7, jit.empty() ? nullptr : jit.data() + 912, A.alpha, rest.data(), nullptr)))
         die_tfft(ctx, rc);
-    if (!tfft_host_open_payload((const uint8_t*)A.pass.data(), A.pass.size(), A.iters, hdr, rest.data(), clen)) {
+    const int opened = raw_key ? tfft_host_open_payload_key(master, hdr, rest.data(), clen)
+                               : tfft_host_open_payload((const uint8_t*)A.pass.data(), A.pass.size(), A.iters, hdr, rest.data(), clen);
+    memset(master, 0, sizeof(master));
+    if (!opened) {
         fprintf(stderr, "Auth failed (wrong pass or data corrupted).\n"); exit(1);  // S:1308
     }
     std::string secret((const char*)rest.data(), clen);
     printf("%s\n", secret.c_str());  // S:1311
-    tfft_host_free(img);
+    tfft_hostlib_free(img);
     tfft_destroy(ctx);
 }
 
@@ -178,8 +205,8 @@ void do_extract(const Args& A) {
 int main(int argc, char** argv) {
     Args A;
     if (!parse(argc, argv, A)) { usage(); return 1; }
-    if (A.mode == "gen-key" || !A.key.empty()) {
-        fprintf(stderr, "turtlefft (B200 build): key management (gen-key / --key) is outside this build; use --pass\n");
+    if (A.mode == "gen-key") {
+        fprintf(stderr, "turtlefft (B200 build): gen-key is outside this build; --key takes keys made by the reference tool\n");
         return 1;
     }
     if (A.adaptive || A.cover_dep) {

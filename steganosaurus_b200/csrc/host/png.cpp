@@ -91,10 +91,13 @@ uint8_t* png_load(const char* path, int* Wout, int* Hout) {
         if (!memcmp(type, "IHDR", 4) && len >= 13) {
             I.W = (int)be32(data); I.H = (int)be32(data + 4); I.depth = data[8]; I.ctype = data[9]; I.interlace = data[12];
             static const int ch[7] = {1, 0, 3, 1, 2, 0, 4};
-            if (I.ctype > 6 || !ch[I.ctype] || I.W <= 0 || I.H <= 0 || data[10] || data[11] || I.interlace > 1) return nullptr;
+            if (have_ihdr || I.ctype > 6 || !ch[I.ctype] || I.W <= 0 || I.H <= 0 || data[10] || data[11] || I.interlace > 1) return nullptr;
+            if (I.W > 16384 || I.H > 16384) return nullptr;  // TFFT_MAX_DIM: nothing larger can be processed (stb caps at 1 << 24)
             if (!(I.depth == 1 || I.depth == 2 || I.depth == 4 || I.depth == 8 || I.depth == 16)) return nullptr;
             I.channels = ch[I.ctype];
             have_ihdr = true;
+        } else if (!have_ihdr) {
+            return nullptr;  // IHDR must come first
         } else if (!memcmp(type, "PLTE", 4)) {
             memcpy(pal, data, len < 768 ? len : 768);
         } else if (!memcmp(type, "IDAT", 4)) {
@@ -122,15 +125,18 @@ uint8_t* png_load(const char* path, int* Wout, int* Hout) {
     std::vector<uint8_t> raw(raw_size);
     z_stream zs{};
     if (inflateInit(&zs) != Z_OK) return nullptr;
-    zs.next_in = idat.data(); zs.avail_in = (uInt)idat.size();
-    size_t produced = 0;
+    size_t produced = 0, fed = 0;
     int zr = Z_OK;
-    while (zr == Z_OK && produced < raw_size) {  // sizes may exceed uInt: feed the output buffer in pieces
+    while (zr == Z_OK && produced < raw_size) {  // sizes may exceed uInt: feed input and output in pieces
+        if (zs.avail_in == 0 && fed < idat.size()) {
+            const size_t take = idat.size() - fed < (1u << 30) ? idat.size() - fed : (1u << 30);
+            zs.next_in = idat.data() + fed; zs.avail_in = (uInt)take; fed += take;
+        }
         const size_t want = raw_size - produced < (1u << 30) ? raw_size - produced : (1u << 30);
         zs.next_out = raw.data() + produced; zs.avail_out = (uInt)want;
         zr = inflate(&zs, Z_NO_FLUSH);
         produced += want - zs.avail_out;
-        if (zs.avail_in == 0 && zr == Z_OK && zs.avail_out != 0) break;
+        if (zs.avail_in == 0 && fed == idat.size() && zr == Z_OK && zs.avail_out != 0) break;
     }
     inflateEnd(&zs);
     if (produced != raw_size) return nullptr;

@@ -140,10 +140,19 @@ static void push_bits(std::vector<uint8_t>& bits, const uint8_t* bytes, size_t n
         }
 }
 
-size_t frame_bits(const uint8_t* pass, size_t plen, const uint8_t salt[16], uint32_t iters, const uint8_t* secret, size_t slen,
-                  uint8_t* bits_out, uint8_t header_out[38]) {
-    uint8_t key[32], nonce[12];
-    derive_keys(pass, plen, salt, iters, key, nonce);
+// --key path (S:576-591): HKDF-Extract(salt, master_key) -> HKDF-Expand("fft_turtle:keys") -> aead_key, nonce
+void derive_keys_raw(const uint8_t master[32], const uint8_t salt[16], uint8_t aead_key[32], uint8_t nonce[12]) {
+    uint8_t prk[32], out[76];
+    hmac_sha256(salt, 16, master, 32, prk);
+    static const char info[] = "fft_turtle:keys";
+    hkdf_expand(prk, (const uint8_t*)info, sizeof(info) - 1, out, sizeof(out));
+    memcpy(aead_key, out + 32, 32);
+    memcpy(nonce, out + 64, 12);
+    memset(prk, 0, sizeof(prk)); memset(out, 0, sizeof(out));
+}
+
+static size_t frame_with(const uint8_t key[32], const uint8_t nonce[12], const uint8_t salt[16], const uint8_t* secret, size_t slen,
+                         uint8_t* bits_out, uint8_t header_out[38]) {
     uint8_t hdr[38] = {'F', 'T', 'T', 'G', 2, 0};  // S:886-904
     memcpy(hdr + 6, salt, 16);
     memcpy(hdr + 22, nonce, 12);
@@ -157,8 +166,25 @@ size_t frame_bits(const uint8_t* pass, size_t plen, const uint8_t salt[16], uint
     push_bits(bits, ct.data(), ct.size(), 7);  // Rep-7 ct|tag (S:991)
     memcpy(bits_out, bits.data(), bits.size());
     if (header_out) memcpy(header_out, hdr, 38);
-    memset(key, 0, sizeof(key));
     return bits.size();
+}
+
+size_t frame_bits(const uint8_t* pass, size_t plen, const uint8_t salt[16], uint32_t iters, const uint8_t* secret, size_t slen,
+                  uint8_t* bits_out, uint8_t header_out[38]) {
+    uint8_t key[32], nonce[12];
+    derive_keys(pass, plen, salt, iters, key, nonce);
+    const size_t n = frame_with(key, nonce, salt, secret, slen, bits_out, header_out);
+    memset(key, 0, sizeof(key));
+    return n;
+}
+
+size_t frame_bits_key(const uint8_t master[32], const uint8_t salt[16], const uint8_t* secret, size_t slen, uint8_t* bits_out,
+                      uint8_t header_out[38]) {
+    uint8_t key[32], nonce[12];
+    derive_keys_raw(master, salt, key, nonce);
+    const size_t n = frame_with(key, nonce, salt, secret, slen, bits_out, header_out);
+    memset(key, 0, sizeof(key));
+    return n;
 }
 
 int parse_header(const uint8_t hdr[38], uint32_t* clen, uint8_t salt[16], uint8_t nonce[12]) {
@@ -176,6 +202,54 @@ int open_payload(const uint8_t* pass, size_t plen, uint32_t iters, const uint8_t
     const bool ok = aead_open(key, nonce, hdr, 38, payload, clen, payload + clen);  // S:1305
     memset(key, 0, sizeof(key));
     return ok ? 1 : 0;
+}
+
+int open_payload_key(const uint8_t master[32], const uint8_t hdr[38], uint8_t* payload, uint32_t clen) {
+    uint8_t key[32], nonce[12];
+    derive_keys_raw(master, hdr + 6, key, nonce);  // S:1275
+    const bool ok = aead_open(key, nonce, hdr, 38, payload, clen, payload + clen);
+    memset(key, 0, sizeof(key));
+    return ok ? 1 : 0;
+}
+
+// decode_or_unwrap_key (S:603-662): base64 of a raw 32-byte key, or of the 80-byte wrapped form
+// "TFKW" | salt[16] | nonce[12] | ct[32] | tag[16] (key and nonce = PBKDF2(wrap_pass, salt, iters, 44), no AAD;
+// the library AEAD copy the reference wraps with carries the same Poly1305 finalisation quirk as its in-TU copy)
+static std::vector<uint8_t> b64_decode(const char* s) {
+    std::vector<uint8_t> out;
+    uint32_t acc = 0;
+    int nb = 0;
+    for (; *s; s++) {
+        const unsigned char c = (unsigned char)*s;
+        int v;
+        if (c >= 'A' && c <= 'Z') v = c - 'A';
+        else if (c >= 'a' && c <= 'z') v = c - 'a' + 26;
+        else if (c >= '0' && c <= '9') v = c - '0' + 52;
+        else if (c == '+') v = 62;
+        else if (c == '/') v = 63;
+        else if (c == '=' || c == '\n' || c == '\r' || c == ' ') continue;
+        else return {};
+        acc = (acc << 6) | (uint32_t)v;
+        nb += 6;
+        if (nb >= 8) { nb -= 8; out.push_back((uint8_t)(acc >> nb)); }
+    }
+    return out;
+}
+int key_decode(const char* key_b64, const char* wrap_pass, uint32_t iters, uint8_t key_out[32]) {
+    const std::vector<uint8_t> d = b64_decode(key_b64);
+    if (d.size() == 80 && !memcmp(d.data(), "TFKW", 4)) {
+        if (!wrap_pass || !*wrap_pass) return -1;  // "Key is wrapped but no unwrap passphrase provided"
+        uint8_t derived[44];
+        pbkdf2((const uint8_t*)wrap_pass, strlen(wrap_pass), d.data() + 4, 16, iters, derived, sizeof(derived));
+        uint8_t ct[32];
+        memcpy(ct, d.data() + 32, 32);
+        const bool ok = aead_open(derived, d.data() + 20, nullptr, 0, ct, 32, d.data() + 64);
+        if (ok) memcpy(key_out, ct, 32);
+        memset(derived, 0, sizeof(derived)); memset(ct, 0, sizeof(ct));
+        return ok ? 1 : 0;
+    }
+    if (d.size() == 32) { memcpy(key_out, d.data(), 32); return 1; }
+    return 0;
 }
 
 }  // namespace tfh

@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(PKG, "libtfft_host.so")
 SYMBOLS = ["tfft_host_sha256", "tfft_host_hmac_sha256", "tfft_host_hkdf_expand", "tfft_host_pbkdf2", "tfft_host_seal",
            "tfft_host_open", "tfft_host_seal_rfc8439", "tfft_host_derive_keys", "tfft_host_turtle_keys", "tfft_host_walk", "tfft_host_jitter",
            "tfft_host_frame_bits", "tfft_host_parse_header", "tfft_host_open_payload", "tfft_host_png_load",
-           "tfft_host_png_save", "tfft_host_free"]
+           "tfft_host_png_save", "tfft_hostlib_free", "tfft_host_derive_keys_raw", "tfft_host_frame_bits_key",
+           "tfft_host_open_payload_key", "tfft_host_key_decode"]
 _lib = None
 _u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 _u32 = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -53,7 +54,14 @@ def load() -> C.CDLL:
     L.tfft_host_png_load.restype = C.POINTER(C.c_uint8)
     L.tfft_host_png_save.argtypes = [cp, _u8, i, i]
     L.tfft_host_png_save.restype = i
-    L.tfft_host_free.argtypes = [C.c_void_p]
+    L.tfft_hostlib_free.argtypes = [C.c_void_p]
+    L.tfft_host_derive_keys_raw.argtypes = [cp, cp, _u8, _u8]
+    L.tfft_host_frame_bits_key.argtypes = [cp, cp, cp, sz, _u8, _u8]
+    L.tfft_host_frame_bits_key.restype = sz
+    L.tfft_host_open_payload_key.argtypes = [cp, cp, _u8, u32]
+    L.tfft_host_open_payload_key.restype = i
+    L.tfft_host_key_decode.argtypes = [cp, cp, u32, _u8]
+    L.tfft_host_key_decode.restype = i
     _lib = L
     return L
 
@@ -142,6 +150,36 @@ def frame_bits(pw: bytes, salt: bytes, iters: int, secret: bytes):
     return bits, hdr.tobytes()
 
 
+# ---- --key path (S:576-591, S:603-662): a 32-byte master key instead of a passphrase; the walk uses
+# turtle_keys(master_key) (path_key = SHA256(master_key), S:1036)
+def key_decode(key_b64: str, wrap_pass: str = "", iters: int = 600000) -> bytes:
+    out = _buf(32)
+    rc = load().tfft_host_key_decode(key_b64.encode(), wrap_pass.encode(), iters, out)
+    if rc != 1:
+        raise ValueError("Failed to decode/unwrap key from --key argument")
+    return out.tobytes()
+
+
+def derive_keys_raw(master: bytes, salt: bytes):
+    k, n = _buf(32), _buf(12)
+    load().tfft_host_derive_keys_raw(master, salt, k, n)
+    return k.tobytes(), n.tobytes()
+
+
+def frame_bits_key(master: bytes, salt: bytes, secret: bytes):
+    n = 912 + 56 * (len(secret) + 16)
+    bits, hdr = _buf(n), _buf(38)
+    got = load().tfft_host_frame_bits_key(master, salt, secret, len(secret), bits, hdr)
+    assert got == n
+    return bits, hdr.tobytes()
+
+
+def open_payload_key(master: bytes, hdr: bytes, payload: bytes, clen: int):
+    d = np.frombuffer(payload, np.uint8).copy()
+    ok = load().tfft_host_open_payload_key(master, hdr, d, clen)
+    return bool(ok), d[:clen].tobytes()
+
+
 def parse_header(hdr: bytes):
     """-> (rc, clen, salt, nonce); rc 1 = 'Magic not found.', 2 = unsupported version (S:1237-1238)."""
     clen = C.c_uint32()
@@ -164,7 +202,7 @@ def png_load(path: str) -> np.ndarray:
     try:
         return np.ctypeslib.as_array(p, shape=(H.value, W.value, 3)).copy()
     finally:
-        load().tfft_host_free(p)
+        load().tfft_hostlib_free(p)
 
 
 def png_save(path: str, rgb) -> None:
@@ -180,13 +218,18 @@ class ExtractError(RuntimeError):
 
 
 def embed_image(ctx, cover, secret: bytes, pw: bytes, alpha=0.5, density=0.7, rmin=0.05, rmax=0.45, magmin=0.01,
-                center=False, pbkdf2_iter=600000, jitter=0.0, salt: bytes | None = None):
-    """do_embed (S:907-1109) for one decoded cover [H,W,3]; returns (stego, nbits)."""
+                center=False, pbkdf2_iter=600000, jitter=0.0, salt: bytes | None = None, key: bytes | None = None):
+    """do_embed (S:907-1109) for one decoded cover [H,W,3]; returns (stego, nbits).  key (32 bytes): the --key path,
+    pw is then ignored."""
     from .api import next_pow2
     H, W, _ = cover.shape
     PH, PW = next_pow2(H), next_pow2(W)
     salt = os.urandom(16) if salt is None else salt  # std::random_device upstream (S:927-929)
-    bits, _ = frame_bits(pw, salt, pbkdf2_iter, secret)
+    if key is not None:
+        bits, _ = frame_bits_key(key, salt, secret)
+        pw = key  # path_key = SHA256(master_key) (S:1036)
+    else:
+        bits, _ = frame_bits(pw, salt, pbkdf2_iter, secret)
     bins = cached_walk(pw, PH, PW, bits.size, rmin, rmax, density)
     jit = jitter_values(pw, bins, jitter) if jitter else None
     stego, usable, _ = ctx.embed_batch(cover[None], bins, bits[None], alpha, center, magmin, rmin, rmax, jitter=jit)
@@ -194,11 +237,13 @@ def embed_image(ctx, cover, secret: bytes, pw: bytes, alpha=0.5, density=0.7, rm
 
 
 def extract_image(ctx, stego, pw: bytes, alpha=0.5, density=0.7, rmin=0.05, rmax=0.45, center=False, pbkdf2_iter=600000,
-                  jitter=0.0) -> bytes:
+                  jitter=0.0, key: bytes | None = None) -> bytes:
     """do_extract (S:1112-1312) for one decoded stego image [H,W,3]; returns the plaintext."""
     from .api import next_pow2
     H, W, _ = stego.shape
     PH, PW = next_pow2(H), next_pow2(W)
+    if key is not None:
+        pw = key
     ctx.forward_batch(stego[None], center)
     hb = cached_walk(pw, PH, PW, 912, rmin, rmax, density)
     hj = jitter_values(pw, hb, jitter) if jitter else None
@@ -210,13 +255,18 @@ def extract_image(ctx, stego, pw: bytes, alpha=0.5, density=0.7, rmin=0.05, rmax
     if rc == 2:
         raise ExtractError(f"Unsupported version ({hdr[4]}).")
     nb = 912 + 56 * (clen + 16)
+    if nb > 3 * PH * PW // 2:  # a length the annulus cannot hold is not a frame (same guard as the CLI and the pipeline)
+        raise ExtractError("Payload truncated after ECC decode.")
     try:  # the reference walks forever on a garbage clen (App. D-8); here the walk is bounded
         allb = cached_walk(pw, PH, PW, nb, rmin, rmax, density)
     except WalkExhausted:
         raise ExtractError("Payload truncated after ECC decode.")
     aj = jitter_values(pw, allb, jitter) if jitter else None
     pay, _ = ctx.read_bits(allb[912:], 7, alpha, jitter=None if aj is None else aj[912:], want_raw=False)
-    ok, pt = open_payload(pw, pbkdf2_iter, hdr, pay[0].tobytes(), clen)
+    if key is not None:
+        ok, pt = open_payload_key(key, hdr, pay[0].tobytes(), clen)
+    else:
+        ok, pt = open_payload(pw, pbkdf2_iter, hdr, pay[0].tobytes(), clen)
     if not ok:
         raise ExtractError("Auth failed (wrong pass or data corrupted).")
     return pt

@@ -26,6 +26,19 @@ def test_cuda_library_exports_header_symbols():
     assert L.tfft_abi_version() == 1
 
 
+def test_the_two_libraries_share_no_symbol():
+    """libtfft_b200.so (tfft_host_alloc / tfft_host_free = pinned CUDA memory) and libtfft_host.so (malloc'd PNG pixels,
+    tfft_hostlib_free) are linked into one process by the CLI: a shared name would make the free() that runs depend on
+    link order."""
+    import subprocess
+    from steganosaurus_b200 import _lib, host
+    def exported(path):
+        out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+        return {ln.split()[-1] for ln in out.splitlines() if " T " in ln and ln.split()[-1].startswith("tfft_")}
+    a, b = exported(_lib.LIB_PATH), exported(host.LIB_PATH)
+    assert a and b and not (a & b), a & b
+
+
 def test_strerror_and_invalid_args_without_gpu():
     from steganosaurus_b200 import _lib
     L = _lib.load()

@@ -16,7 +16,7 @@ def test_exports():
     L = host.load()
     src = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "tfft_host.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    syms = sorted(set(re.findall(r"\b(tfft_host_[a-z0-9_]+)\s*\(", src)))
+    syms = sorted(set(re.findall(r"\b(tfft_host[a-z0-9_]+)\s*\(", src)))
     assert syms == sorted(host.SYMBOLS)
     for s in syms:
         assert hasattr(L, s)
@@ -153,3 +153,68 @@ def test_png_roundtrip_and_pil_interop(tmp_path):
     assert np.array_equal(host.png_load(str(tmp_path / "g16.png"))[:, :, 0], (g16 >> 8).astype(np.uint8))
     with pytest.raises(IOError):
         host.png_load(str(tmp_path / "missing.png"))
+
+
+def test_key_path_against_reference_cli(tmp_path):
+    """--key (S:576-591, S:603-662, S:1020-1040): the reference CLI embeds with a raw / a passphrase-wrapped master key;
+    our host functions (key decode, path keys, AEAD keys) plus the reference's own hot path read the message back."""
+    import subprocess
+    from oracle import pyoracle as O
+    from steganosaurus_b200 import synth
+    if not (O.have_ref() and os.path.exists(O.REF_CLI)):
+        pytest.skip("oracle/_ref not built")
+    r = O.ref()
+    cover = str(tmp_path / "c.png")
+    host.png_save(cover, synth.gen_cover(256, 256, 3))
+    raw_b64 = "AAECAwQFBgcICQoLDA0ODxAREhMUFRYXGBkaGxwdHh8="  # bytes(range(32))
+    assert host.key_decode(raw_b64) == bytes(range(32))
+    with pytest.raises(ValueError):
+        host.key_decode("not base64 !!")
+    with pytest.raises(ValueError):
+        host.key_decode("QUJD")  # 3 bytes
+    # a wrapped key made by the reference's gen-key
+    kf = str(tmp_path / "k.b64")
+    p = subprocess.run([O.REF_CLI, "gen-key", "--key-out", kf, "--wrap-pass", "wrapme", "--pbkdf2_iter", "1000"],
+                       capture_output=True, text=True, timeout=60)
+    assert p.returncode == 0, p.stderr
+    shown = [ln.split("Base64:")[1].strip() for ln in p.stdout.splitlines() if "Base64:" in ln][0]
+    wrapped = open(kf).read().strip()
+    master = host.key_decode(wrapped, "wrapme", 1000)
+    assert master == host.key_decode(shown)
+    with pytest.raises(ValueError):
+        host.key_decode(wrapped, "wrong", 1000)
+    with pytest.raises(ValueError):
+        host.key_decode(wrapped, "", 1000)
+    for key_b64, extra, key in ((raw_b64, [], bytes(range(32))), (wrapped, ["--wrap-pass", "wrapme", "--pbkdf2_iter", "1000"], master)):
+        s = str(tmp_path / "s.png")
+        msg = b"keyed message"
+        p = subprocess.run([O.REF_CLI, "embed", "--in", cover, "--out", s, "--secret", msg.decode(), "--key", key_b64, *extra],
+                           capture_output=True, text=True, timeout=60)
+        assert p.returncode == 0, p.stderr
+        stego = host.png_load(s)
+        nb = 912 + 56 * (len(msg) + 16)
+        bins = host.walk(key, 256, 256, nb)[0]  # path_key = SHA256(master_key)
+        _, raw = r.extract(stego, bins, 1)
+        hdr = r.rep_decode(raw[:912], 3).tobytes()
+        rc, clen, salt, nonce = host.parse_header(hdr)
+        assert (rc, clen) == (0, len(msg))
+        assert host.derive_keys_raw(key, salt)[1] == nonce
+        ok, pt = host.open_payload_key(key, hdr, r.rep_decode(raw[912:], 7).tobytes(), clen)
+        assert ok and pt == msg
+        # and our framing with the header's salt reproduces the embedded bit stream's header
+        bits, hdr2 = host.frame_bits_key(key, salt, msg)
+        assert hdr2 == hdr and bits.size == nb
+
+
+def test_png_load_rejects_hostile_headers(tmp_path):
+    import struct, zlib
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+    sig = b"\x89PNG\r\n\x1a\n"
+    huge = sig + chunk(b"IHDR", struct.pack(">IIBBBBB", 2**31 - 1, 2**31 - 1, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 16)) + chunk(b"IEND", b"")
+    early = sig + chunk(b"IDAT", zlib.compress(b"\0" * 16)) + chunk(b"IHDR", struct.pack(">IIBBBBB", 2, 2, 8, 2, 0, 0, 0)) + chunk(b"IEND", b"")
+    for i, blob in enumerate((huge, early)):
+        p = str(tmp_path / f"bad{i}.png")
+        open(p, "wb").write(blob)
+        with pytest.raises(IOError):
+            host.png_load(p)
