@@ -164,13 +164,14 @@ enum {
     TFFT_K_ROW_FWD = 0,  /* row FFT, u8 -> c64 (fused plane split / centre / zero pad) */
     TFFT_K_COL_FWD = 1,  /* column FFT c64 -> c64 */
     TFFT_K_MEDIAN = 2,   /* median |F| + capacity count */
-    TFFT_K_EMBED = 3,    /* phase scatter */
+    TFFT_K_EMBED = 3,    /* phase scatter (column-resident embed: the per-image bit masks of the fused pass) */
     TFFT_K_COL_INV = 4,  /* column IFFT */
     TFFT_K_ROW_INV = 5,  /* row IFFT + scale/round/clamp/interleave/crop epilogue */
     TFFT_K_EXTRACT = 6,  /* phase gather + vote + pack */
     TFFT_K_C2C = 7,      /* plain c64 pass from the fft2d / fft_pass hooks */
     TFFT_K_COL_FWD_WIN = 8, /* column FFT of an extract: only the columns / rows that hold bins */
-    TFFT_K_COUNT = 9
+    TFFT_K_COL_EMBED = 9,   /* column-resident embed: forward columns + phase write + inverse columns in one pass */
+    TFFT_K_COUNT = 10
 };
 int tfft_profile_enable(tfft_ctx* ctx, int on);
 int tfft_profile_reset(tfft_ctx* ctx);

@@ -26,6 +26,8 @@ struct Slot {
     DevBuf spec, spec2, in, out, bits, med, medians, usable, outbytes, raw;  // spec2: scratch of the four-step passes (dims > 4096)
     DevBuf signmap;  // extract without jitter on 4096-row planes: read bits of every element instead of the spectrum
     DevBuf q32;      // embed on 4096-row half planes: float copy of |F|^2 left by the column pass for the median scan
+                     // (column-resident embed: the two 32-bit planes of the exact q instead, qhi then qlo)
+    DevBuf val;      // column-resident embed: per-image bit masks of the fused pass (embed_val_build)
     // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
     // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
     // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
@@ -55,6 +57,9 @@ struct tfft_ctx {
     bool use_window = true; // extract: the forward column pass keeps only the rows / columns that hold bins (TFFT_EXTRACT_WINDOW=0: all)
     bool use_q32 = true;     // embed, 4096-row half planes: the median scan reads a float copy of |F|^2 (TFFT_SCAN_Q32=0: the spectrum)
     bool use_signmap = true; // extract without jitter, 4096-row planes: the column pass leaves read bits, not spectra (TFFT_SIGNMAP=0)
+    bool use_fused = true;   // embed, 4096-row half planes, no jitter: forward columns + phase write + inverse columns in ONE pass
+                             // (TFFT_FUSED_EMBED=0: the three-kernel sequence col_fwd -> embed_scatter -> col_inv)
+    DevBuf pres;             // ... its per-call bin-presence masks [3][ld/2][512] (shared by the batch)
     unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
     unsigned* h_win = nullptr;  // ... and read back through this pinned pair
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
@@ -260,6 +265,10 @@ int c2c_two_passes(tfft_ctx* ctx, const Launcher& L, PassArgs a, double2* spec, 
 struct BinWindow { int rows = 0, cols = 0, mirrored = 0; };  // mirrored: some bin sits right of the Nyquist column of a half plane
 
 // optional extras of forward_images
+// How an embed call runs its column stage: fused (column-resident, pencil_col_embed_w) when the geometry and the bin list
+// allow it, else forward columns -> embed_scatter -> inverse columns.
+struct EmbedPlan { bool fused = false; int k3max = 0; };
+
 struct FwdOpts {
     unsigned long long* sample_q = nullptr;  // embed, 4096-row half planes: the column pass drops the median sample here
     unsigned sample_stride = 0;
@@ -352,10 +361,64 @@ int inverse_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
     return TFFT_OK;
 }
 
+// Column-resident embed of one chunk: row pass -> [bit masks] -> ONE column pass (forward, phase write, inverse; leaves
+// q = |F|^2 as two word planes + the median sample) -> median / capacity on the q planes -> inverse row pass ->
+// pass-through of the images over capacity (the phase write was speculative, S:1009-1012).
+int embed_chunk_fused(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cover, int nimg, const Geom& g,
+                      const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits, double alpha, int center, double magmin,
+                      double rmin, double rmax, uint8_t* d_stego, uint64_t* d_usable, double* d_median, const EmbedPlan& plan) {
+    int rc;
+    MedianWork mw;
+    median_work_carve(mw, S.med.p, nimg * 3, cand_cap_for(g.P));
+    const double cols = (double)g.ld;
+    const size_t E = g.E;
+    if ((rc = ensure(ctx, S.q32, (size_t)nimg * 3 * E * 2 * sizeof(uint32_t)))) return rc;
+    if (nbits && (rc = ensure(ctx, S.val, embed_mask_bytes(g.ld, nimg * 3)))) return rc;
+    uint32_t* qhi = (uint32_t*)S.q32.p;
+    uint32_t* qlo = qhi + (size_t)nimg * 3 * E;
+    PassArgs a = base_args(ctx, (double2*)S.spec.p, nimg, g, center);
+    a.img_in = d_cover; a.axis = 0; a.log2n = g.lw; a.inverse = 0; a.in_rows = g.H;
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    if (nbits) {
+        ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * ((double)nbits * 5.0 + 2.0 * (double)embed_mask_bytes(g.ld, 3)));
+        CK(launch_embed_val(L, d_bins, d_bits, nbits, nimg, g.lay(), (uint16_t*)S.val.p));
+    }
+    a.img_in = nullptr; a.axis = 1; a.log2n = g.lh; a.PW = g.ld; a.half = 0;
+    a.in_rows = g.H; a.out_rows = g.H;   // rows >= H: zero on input (S:395), cropped on output (S:399-403)
+    a.fused_embed = 1;
+    a.sample_q = (unsigned long long*)mw.cand; a.sample_stride = mw.cand_cap;
+    a.qhi = qhi; a.qlo = qlo;
+    a.embed_pres = nbits ? (const uint16_t*)ctx->pres.p : nullptr;
+    a.embed_val = nbits ? (const uint16_t*)S.val.p : nullptr;
+    a.embed_k3max = plan.k3max;
+    a.embed_cos = cos(alpha); a.embed_sin = sin(alpha);
+    { ProfScope ps(ctx, L.stream, TFFT_K_COL_EMBED,
+                   (double)nimg * 3.0 * (32.0 * (double)g.H * cols + 8.0 * (double)g.PH * cols + (nbits ? 2.0 * (cols / 2.0) * 512.0 * 2.0 : 0.0)));
+      CK(launch_fft_pass(L, a)); }
+    const int m = std::min(g.PH, g.PW);
+    const unsigned presampled = col_pass_samples(g.PH, g.PW, g.half);
+    { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 4.0 * (double)E);
+      CK(launch_median_capacity(L, nullptr, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable, presampled, nullptr, qhi, qlo)); }
+    a.fused_embed = 0; a.sample_q = nullptr; a.qhi = nullptr; a.qlo = nullptr;
+    a.PW = g.PW; a.half = g.half; a.axis = 0; a.log2n = g.lw; a.inverse = 1; a.img_out = d_stego;
+    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_INV, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    if (nbits) CK(launch_passthrough(L, d_cover, d_stego, g.img_bytes, nimg, d_usable, nbits));
+    return TFFT_OK;
+}
+
+// can this call's column stage run fused?  (geometry part; the bin list part is decided by the callers)
+bool fused_geometry_ok(const tfft_ctx* ctx, const Launcher& L, const Geom& g, const double* jitter) {
+    return ctx->use_fused && ctx->col_sample && !jitter && !g.large && !g.col4 && g.half && g.lh == 12 && ctx->fft_impl == 1 &&
+           fused_embed_supported(L) && col_pass_samples(g.PH, g.PW, g.half) <= cand_cap_for(g.P);
+}
+
 int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cover, int nimg, const Geom& g,
                 const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits, const double* d_jitter,
                 double alpha, int center, double magmin, double rmin, double rmax,
-                uint8_t* d_stego, uint64_t* d_usable, double* d_median) {
+                uint8_t* d_stego, uint64_t* d_usable, double* d_median, const EmbedPlan& plan = EmbedPlan{}) {
+    if (plan.fused)
+        return embed_chunk_fused(ctx, L, S, d_cover, nimg, g, d_bins, d_bits, nbits, alpha, center, magmin, rmin, rmax, d_stego, d_usable,
+                                 d_median, plan);
     double2* spec = nullptr;  // whichever of the slot's two buffers holds the spectrum
     MedianWork mw;
     median_work_carve(mw, S.med.p, nimg * 3, cand_cap_for(g.P));
@@ -455,6 +518,21 @@ bool bins_ok(const uint32_t* bins, size_t n, size_t P) {
         if ((bins[i] >> 30) > 2 || (size_t)(bins[i] & 0x3FFFFFFFu) >= P) return false;
     return true;
 }
+// ... plus what the column-resident embed needs: every bin strictly between column 0 and the Nyquist column (the half
+// layout then stores exactly the bin itself, never its mirror) and the largest row block
+bool bins_ok_fused(const uint32_t* bins, size_t n, const Geom& g, bool& fusable, int& k3max) {
+    uint32_t bad = 0, unf = 0, ry = 0;
+    const uint32_t P = (uint32_t)std::min<size_t>(g.P, 0x40000000u), xmask = (uint32_t)(g.PW - 1), half = (uint32_t)(g.PW >> 1);
+    for (size_t i = 0; i < n; i++) {
+        const uint32_t lin = bins[i] & 0x3FFFFFFFu, x = lin & xmask;
+        bad |= (uint32_t)((bins[i] >> 30) > 2) | (uint32_t)(lin >= P);
+        unf |= (uint32_t)(x == 0) | (uint32_t)(x >= half);
+        ry = std::max(ry, lin >> g.lw);
+    }
+    fusable = !bad && !unf;
+    k3max = (int)(ry >> 8);
+    return !bad;
+}
 // the same check plus the window of the workspace the list touches (same rule as the bins_window kernel)
 bool bins_ok_window(const uint32_t* bins, size_t n, const Geom& g, BinWindow& w) {
     uint32_t bad = 0, ry = 0, rx = 0;
@@ -547,6 +625,7 @@ int tfft_create(int device, tfft_ctx** out) {
     if (const char* ew = getenv("TFFT_EXTRACT_WINDOW")) ctx->use_window = atoi(ew) != 0;
     if (const char* sm = getenv("TFFT_SIGNMAP")) ctx->use_signmap = atoi(sm) != 0;
     if (const char* sq = getenv("TFFT_SCAN_Q32")) ctx->use_q32 = atoi(sq) != 0;
+    if (const char* fe = getenv("TFFT_FUSED_EMBED")) ctx->use_fused = atoi(fe) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
     if (e == cudaSuccess) e = cudaMalloc((void**)&ctx->d_tw, sizeof(double2) * (TW_N / 2));
@@ -565,11 +644,11 @@ void tfft_destroy(tfft_ctx* ctx) {
     for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
         release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.med);
-        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap); release(S.q32);
+        release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap); release(S.q32); release(S.val);
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
-    release(ctx->bins); release(ctx->jitter); release(ctx->full);
+    release(ctx->bins); release(ctx->jitter); release(ctx->full); release(ctx->pres);
     prof_drain(ctx);
     for (cudaEvent_t ev : ctx->prof_pool) cudaEventDestroy(ev);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
@@ -599,7 +678,7 @@ int tfft_profile_read(tfft_ctx* ctx, int kind, uint64_t* groups, double* total_m
 }
 const char* tfft_kind_name(int kind) {
     static const char* names[TFFT_K_COUNT] = {"row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter",
-                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window"};
+                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused"};
     return (kind >= 0 && kind < TFFT_K_COUNT) ? names[kind] : "?";
 }
 
@@ -626,12 +705,28 @@ int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, in
     Slot& S = ctx->slot[0];
     if ((rc = ensure_slot(ctx, S, g, chunk, false, 0, 0, 0))) return rc;
     Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    EmbedPlan plan;
+    if (fused_geometry_ok(ctx, L, g, d_jitter)) {
+        // the bin list lives on the device: one reduction + ONE stream synchronisation per call decides (as the extracts do)
+        plan.fused = true;
+        if (nbits) {
+            CK(launch_embed_bins_check(L, d_bins, nbits, g.lay(), ctx->d_win));
+            CK(cudaMemcpyAsync(ctx->h_win, ctx->d_win, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, L.stream));
+            CK(cudaStreamSynchronize(L.stream));
+            plan.fused = ctx->h_win[0] == 0;
+            plan.k3max = (int)(ctx->h_win[1] >> 8);
+            if (plan.fused) {
+                if ((rc = ensure(ctx, ctx->pres, embed_mask_bytes(g.ld, 3)))) return rc;
+                CK(launch_embed_pres(L, d_bins, nbits, g.lay(), (uint16_t*)ctx->pres.p));
+            }
+        }
+    }
     for (int i0 = 0; i0 < n; i0 += chunk) {
         const int m = std::min(chunk, n - i0);
         uint64_t* us = d_usable ? d_usable + i0 : (uint64_t*)S.usable.p;
         double* med = d_median ? d_median + (size_t)i0 * 3 : (double*)S.medians.p;
         rc = embed_chunk(ctx, L, S, d_cover + (size_t)i0 * g.img_bytes, m, g, d_bins, d_bits + (size_t)i0 * nbits, nbits,
-                         d_jitter, alpha, center, magmin, rmin, rmax, d_stego + (size_t)i0 * g.img_bytes, us, med);
+                         d_jitter, alpha, center, magmin, rmin, rmax, d_stego + (size_t)i0 * g.img_bytes, us, med, plan);
         if (rc) return rc;
     }
     return TFFT_OK;
@@ -646,14 +741,22 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
     if (n == 0) return TFFT_OK;
-    if (!bins_ok(bins, nbits, g.P)) return TFFT_E_INVALID;
+    bool fusable = false;
+    EmbedPlan plan;
+    if (!bins_ok_fused(bins, nbits, g, fusable, plan.k3max)) return TFFT_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     ctx->res_n = 0;
+    plan.fused = fusable && fused_geometry_ok(ctx, make_launcher(ctx, ctx->slot[0].stream), g, jitter);
     const int chunk = std::min(chunk_for(ctx, g, n, HOST_SLOTS), HOST_CHUNK);
     const int nslots = std::min(HOST_SLOTS, (n + chunk - 1) / chunk);
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
+    if (plan.fused && nbits) {  // bin-presence masks of the fused pass: once per call, read by every slot stream
+        if ((rc = ensure(ctx, ctx->pres, embed_mask_bytes(g.ld, 3)))) return rc;
+        CK(launch_embed_pres(make_launcher(ctx, ctx->slot[0].stream), (const uint32_t*)ctx->bins.p, nbits, g.lay(), (uint16_t*)ctx->pres.p));
+        CK(cudaStreamSynchronize(ctx->slot[0].stream));
+    }
     const size_t stage_bytes = (size_t)chunk * (sizeof(uint64_t) + 3 * sizeof(double));
     for (int s = 0; s < nslots; s++)
         if ((rc = ensure_stage(ctx, ctx->slot[s], stage_bytes))) return rc;
@@ -686,7 +789,7 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
         Launcher L = make_launcher(ctx, st);
         rc = embed_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, (const uint8_t*)S.bits.p, nbits,
                          jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, magmin, rmin, rmax,
-                         (uint8_t*)S.out.p, (uint64_t*)S.usable.p, (double*)S.medians.p);
+                         (uint8_t*)S.out.p, (uint64_t*)S.usable.p, (double*)S.medians.p, plan);
         if (rc) return rc;
         CK(cudaMemcpyAsync(stego + (size_t)i0 * g.img_bytes, S.out.p, (size_t)m * g.img_bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(S.h_stage, S.usable.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, st));

@@ -609,6 +609,23 @@ __device__ __forceinline__ void scan_stage(bool member, double2 z, MedianWork& w
     }
 }
 
+// the same with the key given (q-plane scan: keys are the bit patterns of q = |F|^2)
+__device__ __forceinline__ void scan_stage_key(bool member, uint64_t key, MedianWork& w, int ip, uint64_t* s_buf, unsigned* s_cnt) {
+    const int lane = threadIdx.x & 31;
+    const unsigned m = __ballot_sync(0xffffffffu, member);
+    unsigned b0 = 0;
+    if (lane == 0) b0 = atomicAdd(s_cnt, (unsigned)__popc(m));
+    b0 = __shfl_sync(0xffffffffu, b0, 0);
+    if (member) {
+        const unsigned slot = b0 + __popc(m & ((1u << lane) - 1));
+        if (slot < SCAN_SBUF) s_buf[slot] = key;
+        else {
+            const unsigned g = atomicAdd(&w.cand_n[ip], 1u);
+            if (g < w.cand_cap) w.cand[(size_t)ip * w.cand_cap + g] = key;
+        }
+    }
+}
+
 // Truly rare (~1e-4 of the bins at magmin = 0.01): a capacity-relevant magnitude.
 __device__ __noinline__ void scan_cap_rare(double2 z, double q, uint64_t i, const SpecLayout& lay, const ScanCap& cap, double qcap_lo,
                                            MedianWork& w, int ip, unsigned& capb) {
@@ -837,6 +854,217 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q32(const float4*
         if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
 }
 
+
+// The scan over the two 32-bit planes of q the column-resident embed pass leaves behind (PassArgs::qhi / qlo, the layout
+// of q32: word index ((g * 16 + k1) * 4 + j) * 128 + 4 lane + e holds row k1 + 16 m + 256 (4 j + e) of column 2 g + c,
+// lane = 2 m + c).  Non-negative doubles order like their bit patterns, so the top word alone decides every element
+// whose top word differs from those of the bracket edges; the rest (and the capacity-relevant tiny ones) are queued per
+// warp and settled on the exact double (top and low word gathered) -- the same counts and members as a scan of q itself.
+// Keys are the bit patterns of q; the median is sqrt() of the selected one (median_members / capacity_resolve, qkeys = 1).
+__device__ __forceinline__ void q64_coords(unsigned li, int& y, int& x) {
+    const unsigned e = li & 3u, i4 = li >> 2;
+    const int ln = (int)(i4 & 31u), j = (int)((i4 >> 5) & 3u), k1 = (int)((i4 >> 7) & 15u), g = (int)(i4 >> 11);
+    x = 2 * g + (ln & 1);
+    y = k1 + 16 * (ln >> 1) + 1024 * j + 256 * (int)e;
+}
+__device__ __noinline__ void scan_cap_rare_q(uint64_t key, double q, unsigned li, const SpecLayout& lay, const ScanCap& cap, double qcap_lo,
+                                             MedianWork& w, int ip, unsigned& capb) {
+    int y, x;
+    q64_coords(li, y, x);
+    if (!col_weight(lay, x)) return;  // pad column
+    const bool axis = y == 0 || x == 0 || y == (lay.PH >> 1) || x == (lay.PW >> 1);  // on_axis S:698 (even sizes)
+    const double r = sqrt((double)((long long)y * y + (long long)x * x));
+    if (axis || r < cap.rlo || r > cap.rhi) return;
+    if (q < qcap_lo) capb++;
+    else {
+        const unsigned g = atomicAdd(&w.cap_unc_n[ip], 1u);
+        if (g < CAP_UNC_MAX) w.cap_unc[(size_t)ip * CAP_UNC_MAX + g] = key;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS, 2) median_scan_q64(const uint4* __restrict__ qhi, const uint32_t* __restrict__ qlo, SpecLayout lay,
+                                                                MedianWork w, const Bracket* __restrict__ br, ScanCap cap) {
+    __shared__ uint64_t s_buf[SCAN_SBUF];
+    __shared__ uint32_t s_q[SCAN_THREADS / 32][Q32_WQ];  // element index (24 bits) | counted as below (bit 28) | weight (bits 30..31)
+    __shared__ unsigned s_cnt, s_base;
+    __shared__ long long ws[SCAN_THREADS / 32];
+    __shared__ unsigned wc[SCAN_THREADS / 32];
+    const int ip = blockIdx.y;
+    const uint64_t E = lay.plane_elems(), E4 = E / 4;
+    const uint4* hp = qhi + (size_t)ip * E4;
+    const uint32_t* hw = (const uint32_t*)hp;
+    const uint32_t* lw = qlo + (size_t)ip * E;
+    const double qlo_d = br[ip].qlo, qhi_d = br[ip].qhi;
+    const double qcap_lo = cap.on ? cap.magmin2 * qlo_d * (1.0 - 1e-9) : 0.0;
+    const double qcap_hi = cap.on ? cap.magmin2 * qhi_d * (1.0 + 1e-9) : -1.0;
+    // top words of the edges: below hlo -> certainly q < qlo; above hhi -> certainly q > qhi; at most hcap -> look
+    const unsigned hlo = (unsigned)__double2hiint(qlo_d), hhi = (unsigned)__double2hiint(qhi_d);
+    const bool capon = cap.on && qcap_hi >= 0.0;
+    const unsigned hcap = capon ? (unsigned)__double2hiint(qcap_hi) : 0u;
+    const int hcols = lay.PW >> 1;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    long long acc = 0;
+    unsigned capb = 0;
+    const int lane = threadIdx.x & 31;
+    uint32_t* myq = s_q[threadIdx.x >> 5];
+    constexpr uint32_t TILE4 = SCAN_THREADS * SCAN_UNROLL;
+    const uint64_t ntiles = (E4 + TILE4 - 1) / TILE4;
+    for (uint64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const uint64_t base = t * TILE4 + threadIdx.x;
+        uint4 f[SCAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const uint64_t i4 = base + (uint64_t)u * SCAN_THREADS;
+            f[u] = i4 < E4 ? __ldcs(hp + i4) : make_uint4(~0u, ~0u, ~0u, ~0u);  // all ones: above everything
+        }
+        unsigned look = 0, counted = 0;
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; u++) {
+            const uint64_t i4 = base + (uint64_t)u * SCAN_THREADS;
+            const int x = 2 * (int)(i4 >> 11) + (int)(i4 & 1);
+            const int wgt = (x == 0 || x == hcols) ? 1 : (x < hcols ? 2 : 0);
+            const unsigned hv[4] = {f[u].x, f[u].y, f[u].z, f[u].w};
+            unsigned nb = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const bool b = hv[e] < hlo;
+                nb += b ? 1u : 0u;
+                counted |= b ? (1u << (4 * u + e)) : 0u;
+                look |= (wgt != 0 && ((hv[e] >= hlo && hv[e] <= hhi) || (capon && hv[e] <= hcap))) ? (1u << (4 * u + e)) : 0u;
+            }
+            acc += (long long)(nb * (unsigned)wgt);
+        }
+        const unsigned cnt = __popc(look);
+        unsigned incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        const unsigned nq_all = __shfl_sync(0xffffffffu, incl, 31);
+        if (nq_all == 0) continue;  // (warp-uniform)
+        unsigned pos = incl - cnt;
+        while (look) {
+            const int bit = __ffs(look) - 1;
+            look &= look - 1;
+            const uint64_t i4 = base + (uint64_t)(bit >> 2) * SCAN_THREADS;
+            const int x = 2 * (int)(i4 >> 11) + (int)(i4 & 1);
+            const unsigned wgt = (x == 0 || x == hcols) ? 1u : 2u;  // (pad columns never get here)
+            if (pos < Q32_WQ) myq[pos] = (unsigned)(i4 * 4 + (unsigned)(bit & 3)) | (((counted >> bit) & 1u) << 28) | (wgt << 30);
+            pos++;
+        }
+        __syncwarp();
+        const unsigned nq = nq_all < Q32_WQ ? nq_all : Q32_WQ;
+        if (nq_all > Q32_WQ && lane == 0) { w.flags[0] = 1; w.flags[1] = 1; }  // hopeless bracket: the exact generic passes take over
+        for (unsigned i = lane; i - lane < nq; i += 32) {
+            const bool valid = i < nq;
+            const unsigned ent = valid ? myq[i] : 0u;
+            const unsigned li = ent & 0xFFFFFFu, wgt = ent >> 30;
+            bool member = false;
+            uint64_t key = 0;
+            if (valid) {
+                const unsigned hi = hw[li], lo = lw[li];
+                key = ((uint64_t)hi << 32) | lo;
+                const double q = __hiloint2double((int)hi, (int)lo);
+                const bool lowq = q < qlo_d;
+                member = !lowq && q <= qhi_d;
+                if (lowq && !((ent >> 28) & 1u)) acc += wgt;  // (the top word alone did not count it)
+                if (q <= qcap_hi) scan_cap_rare_q(key, q, li, lay, cap, qcap_lo, w, ip, capb);
+                if (member && wgt == 1) {
+                    const unsigned gb = atomicAdd(&w.cand_b_n[ip], 1u);
+                    if (gb < CAND_B_MAX) w.cand_b[(size_t)ip * CAND_B_MAX + gb] = key;
+                }
+            }
+            if (__any_sync(0xffffffffu, member)) scan_stage_key(member, key, w, ip, s_buf, &s_cnt);
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o; o >>= 1) { acc += __shfl_down_sync(0xffffffffu, acc, o); capb += __shfl_down_sync(0xffffffffu, capb, o); }
+    if (lane == 0) { ws[threadIdx.x >> 5] = acc; wc[threadIdx.x >> 5] = capb; }
+    __syncthreads();
+    const unsigned nloc = s_cnt < SCAN_SBUF ? s_cnt : SCAN_SBUF;
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        unsigned c = 0;
+        for (int k = 0; k < SCAN_THREADS / 32; k++) { t += ws[k]; c += wc[k]; }
+        if (t) atomicAdd((unsigned long long*)&w.counts[ip], (unsigned long long)t);
+        if (c) atomicAdd((unsigned long long*)&w.cap_below[ip], (unsigned long long)c);
+        s_base = nloc ? atomicAdd(&w.cand_n[ip], nloc) : 0;
+    }
+    __syncthreads();
+    uint64_t* cand = w.cand + (size_t)ip * w.cand_cap;
+    for (unsigned i = threadIdx.x; i < nloc; i += blockDim.x)
+        if (s_base + i < w.cand_cap) cand[s_base + i] = s_buf[i];
+}
+
+// generic (fallback) radix pass over the q planes: histogram of digit d of the keys (bit patterns of q)
+__global__ void __launch_bounds__(512) median_hist_q64(const uint32_t* __restrict__ qhi, const uint32_t* __restrict__ qlo, SpecLayout lay, int d,
+                                                       MedianWork w, const int* gate) {
+    __shared__ uint32_t sh[RADIX];
+    if (gate && !*gate) return;
+    const int ip = blockIdx.y;
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint64_t E = lay.plane_elems();
+    const uint32_t* hw = qhi + (size_t)ip * E;
+    const uint32_t* lw = qlo + (size_t)ip * E;
+    const int sft = key_shift(d), wid = key_width(d);
+    const uint64_t prefix = w.prefix[ip];
+    const int hi_sft = sft + wid;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (uint64_t)gridDim.x * blockDim.x) {
+        int y, x;
+        q64_coords((unsigned)i, y, x);
+        const int wt = col_weight(lay, x);
+        if (!wt) continue;
+        const uint64_t k = ((uint64_t)hw[i] << 32) | lw[i];
+        if (d == 0 || (k >> hi_sft) == (prefix >> hi_sft))
+            atomicAdd(&sh[(unsigned)(k >> sft) & ((1u << wid) - 1)], (unsigned)wt);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&w.hist[ip * RADIX + i], sh[i]);
+}
+// q keys -> magnitudes, for every plane (the selection ran on the bit patterns of q)
+__global__ void median_sqrt_keys(double* median, int nplanes) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip < nplanes) median[ip] = sqrt(median[ip]);
+}
+// element index of (y, x) in the q planes of a 4096-row half plane
+__device__ __forceinline__ unsigned q64_index(int y, int x) {
+    const unsigned g = (unsigned)x >> 1, c = (unsigned)x & 1u, k1 = (unsigned)y & 15u, m = ((unsigned)y >> 4) & 15u, k3 = (unsigned)y >> 8;
+    const unsigned i4 = ((g * 16 + k1) * 4 + (k3 >> 2)) * 32 + 2 * m + c;
+    return i4 * 4 + (k3 & 3u);
+}
+__global__ void __launch_bounds__(256) capacity_count_q64(const uint32_t* __restrict__ qhi, const uint32_t* __restrict__ qlo, SpecLayout lay, int ymax,
+                                                          int xmax, double rlo, double rhi, double magmin, const double* __restrict__ median,
+                                                          uint64_t* counts, const int* gate) {
+    if (gate && !*gate) return;
+    const int ip = blockIdx.y;
+    const int PH = lay.PH, PW = lay.PW;
+    const double thr = magmin * median[ip];
+    const uint64_t E = lay.plane_elems();
+    const uint32_t* hw = qhi + (size_t)ip * E;
+    const uint32_t* lw = qlo + (size_t)ip * E;
+    const long long box = (long long)(ymax + 1) * (xmax + 1);
+    unsigned local = 0;
+    const unsigned bw = (unsigned)(xmax + 1);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < box; i += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)((unsigned)i / bw), x = (int)((unsigned)i % bw);
+        if (y == 0 || x == 0 || y == PH / 2 || x == PW / 2) continue;
+        const double r = sqrt((double)((long long)y * y + (long long)x * x));
+        if (r < rlo || r > rhi) continue;
+        const unsigned li = q64_index(y, x);
+        if (sqrt(__hiloint2double((int)hw[li], (int)lw[li])) < thr) continue;  // abs(F) < t (S:1004)
+        local++;
+    }
+    for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    __shared__ unsigned ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) t += ws[i];
+        if (t) atomicAdd((unsigned long long*)&counts[ip], (unsigned long long)t);
+    }
+}
+
 // one CTA per plane: exact rank among the members, or raise the fallback flag
 __global__ void __launch_bounds__(1024) median_members(MedianWork w, uint64_t P, uint32_t wa, double* median, int* flag, uint32_t guard) {
     __shared__ SelectScratch sc;
@@ -900,7 +1128,7 @@ __global__ void capacity_finish(const uint64_t* counts, uint64_t* usable, int ni
 // threshold magmin*median (abs(F) < t, S:1004).  A plane whose list overflowed raises flags[1] and the
 // whole batch is recounted by capacity_count.
 __global__ void __launch_bounds__(128) capacity_resolve(MedianWork w, int nplanes, double magmin, const double* __restrict__ median,
-                                                        uint64_t ann_total) {
+                                                        uint64_t ann_total, int qkeys) {
     const int ip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (ip >= nplanes) return;
     const uint32_t n = w.cap_unc_n[ip];
@@ -910,8 +1138,11 @@ __global__ void __launch_bounds__(128) capacity_resolve(MedianWork w, int nplane
     }
     const double thr = magmin * median[ip];
     unsigned c = 0;
-    for (uint32_t i = lane; i < n; i += 32)
-        c += __longlong_as_double((long long)w.cap_unc[(size_t)ip * CAP_UNC_MAX + i]) < thr ? 1u : 0u;
+    for (uint32_t i = lane; i < n; i += 32) {
+        double v = __longlong_as_double((long long)w.cap_unc[(size_t)ip * CAP_UNC_MAX + i]);
+        if (qkeys) v = sqrt(v);  // keys from the q planes are |F|^2
+        c += v < thr ? 1u : 0u;
+    }
     for (int o = 16; o; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
     if (lane == 0) w.counts[ip] = ann_total - w.cap_below[ip] - c;
 }
@@ -946,7 +1177,10 @@ static uint64_t annulus_total_host(int PH, int PW, int ymax, int xmax, double rl
 
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable, unsigned presampled, const float* q32) {
+                                   double* d_median, uint64_t* d_usable, unsigned presampled, const float* q32,
+                                   const uint32_t* qhi, const uint32_t* qlo) {
+    const bool q64 = qhi != nullptr && qlo != nullptr;  // no spectrum: everything runs on the two word planes of q
+    if (q64 && !(lay.half && lay.PH == 4096 && presampled)) return cudaErrorInvalidValue;
     const int PH = lay.PH, PW = lay.PW;
     const uint64_t P = (uint64_t)PH * PW;        // size of the full multiset (ranks refer to it)
     const uint64_t E = lay.plane_elems();        // stored elements per plane
@@ -987,7 +1221,12 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         unsigned cc = cap_env ? cap_env : (unsigned)((ntiles + 6) / 7);
         if (cc < 1) cc = 1;
         const unsigned per_plane = (unsigned)(ntiles < cc ? ntiles : cc);
-        if (q32 && lay.half && PH == 4096 && !all) {
+        if (q64) {
+            const uint64_t nt4 = (E / 4 + SCAN_TILE - 1) / SCAN_TILE;
+            unsigned c4 = cap_env ? cap_env : (unsigned)((nt4 + 1) / 2);
+            if (c4 < 1) c4 = 1;
+            median_scan_q64<<<dim3((unsigned)(nt4 < c4 ? nt4 : c4), (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>((const uint4*)qhi, qlo, lay, w, br, cap);
+        } else if (q32 && lay.half && PH == 4096 && !all) {
             const uint64_t nt4 = (E / 4 + SCAN_TILE - 1) / SCAN_TILE;  // tiles of float4 (four elements each)
             unsigned c4 = cap_env ? cap_env : (unsigned)((nt4 + 1) / 2);  // ~2 tiles (32 K elements) per CTA, as above
             if (c4 < 1) c4 = 1;
@@ -1004,13 +1243,18 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
     {
         const dim3 fgrid(8, (unsigned)nplanes);  // rarely does real work: keep the gated launches cheap
         for (int d = 0; d < NUM_DIGITS; d++) {
-            median_hist<<<fgrid, 512, 0, L.stream>>>(spec, lay, d, w, d_flag);
+            if (q64) median_hist_q64<<<fgrid, 512, 0, L.stream>>>(qhi, qlo, lay, d, w, d_flag);
+            else median_hist<<<fgrid, 512, 0, L.stream>>>(spec, lay, d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
             median_pick<<<nplanes, 256, 0, L.stream>>>(d, w, d_flag);
             TFFT_LAUNCH_CHECK(L);
         }
         median_from_prefix<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w, d_median, nplanes, d_flag);
         TFFT_LAUNCH_CHECK(L);
+        if (q64) {  // the selection ran on q = |F|^2
+            median_sqrt_keys<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(d_median, nplanes);
+            TFFT_LAUNCH_CHECK(L);
+        }
     }
     if (d_usable) {
         const long long box = (long long)(ymax + 1) * (xmax + 1);
@@ -1020,17 +1264,19 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         const dim3 cgrid((unsigned)cb, (unsigned)nplanes);
         if (cap.on) {
             const uint64_t ann = annulus_total_host(PH, PW, ymax, xmax, rlo, rhi);
-            capacity_resolve<<<(nplanes + 3) / 4, 128, 0, L.stream>>>(w, nplanes, magmin, d_median, ann);
+            capacity_resolve<<<(nplanes + 3) / 4, 128, 0, L.stream>>>(w, nplanes, magmin, d_median, ann, q64 ? 1 : 0);
             TFFT_LAUNCH_CHECK(L);
             capacity_zero_gated<<<(nplanes + 255) / 256, 256, 0, L.stream>>>(w.counts, nplanes, d_flag + 1);
             TFFT_LAUNCH_CHECK(L);
             // gated recount: almost never does real work, so keep the launch small (grid-stride loop inside)
-            capacity_count<<<dim3(cgrid.x < 16 ? cgrid.x : 16, cgrid.y), 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, d_flag + 1);
+            if (q64) capacity_count_q64<<<dim3(cgrid.x < 16 ? cgrid.x : 16, cgrid.y), 256, 0, L.stream>>>(qhi, qlo, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, d_flag + 1);
+            else capacity_count<<<dim3(cgrid.x < 16 ? cgrid.x : 16, cgrid.y), 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, d_flag + 1);
             TFFT_LAUNCH_CHECK(L);
         } else {
             cudaError_t e = cudaMemsetAsync(w.counts, 0, sizeof(uint64_t) * nplanes, L.stream);
             if (e != cudaSuccess) return e;
-            capacity_count<<<cgrid, 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, nullptr);
+            if (q64) capacity_count_q64<<<cgrid, 256, 0, L.stream>>>(qhi, qlo, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, nullptr);
+            else capacity_count<<<cgrid, 256, 0, L.stream>>>(spec, lay, ymax, xmax, rlo, rhi, magmin, d_median, w.counts, nullptr);
             TFFT_LAUNCH_CHECK(L);
         }
         capacity_finish<<<(nplanes / 3 + 255) / 256, 256, 0, L.stream>>>(w.counts, d_usable, nplanes / 3);
@@ -1088,6 +1334,96 @@ cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout 
     if (nbits == 0 || nimg == 0) return cudaSuccess;
     dim3 grid((unsigned)((nbits + 255) / 256), (unsigned)nimg);
     embed_scatter<<<grid, 256, 0, L.stream>>>(spec, lay, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+
+// --------------------------------------------------------------------------------------------
+// Inputs of the column-resident embed pass (pencil_col_embed_w, tfft_pencil.cu): the bin list as one 16-bit mask per
+// thread and column pair.  Thread tid = 2 (16 k1 + m) + c of pair g owns rows k1 + 16 m + 256 k3 of column 2 g + c, so
+// bin (plane, y, x) is bit k3 = y >> 8 of slot ((plane * groups + x >> 1) * 512 + 2 (16 (y & 15) + (y >> 4 & 15)) + (x & 1)).
+// pres: which bins exist (built once per call, the list is shared by the batch); val: the bit to write (per image).
+// Bins are unique (Turtle::mark_here S:805-809), so every mask bit has one writer.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed_slot(uint32_t b, int lw, int groups, size_t& word, unsigned& shift) {
+    const uint32_t lin = b & 0x3FFFFFFFu, p = b >> 30;
+    const unsigned y = lin >> lw, x = lin & ((1u << lw) - 1u);
+    const unsigned tid = ((((y & 15u) << 4) | ((y >> 4) & 15u)) << 1) | (x & 1u);
+    const size_t s = ((size_t)p * groups + (x >> 1)) * 512 + tid;
+    word = s >> 1;
+    shift = (y >> 8) + 16u * (unsigned)(s & 1);
+}
+__global__ void __launch_bounds__(256) embed_pres_build(const uint32_t* __restrict__ bins, size_t nbits, int lw, int groups, uint32_t* pres32) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbits) return;
+    size_t word; unsigned shift;
+    embed_slot(bins[i], lw, groups, word, shift);
+    atomicOr(pres32 + word, 1u << shift);
+}
+__global__ void __launch_bounds__(256) embed_val_build(const uint32_t* __restrict__ bins, const uint8_t* __restrict__ bits, size_t nbits, int lw,
+                                                       int groups, uint32_t* val32) {
+    const int img = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbits || !bits[(size_t)img * nbits + i]) return;
+    size_t word; unsigned shift;
+    embed_slot(bins[i], lw, groups, word, shift);
+    atomicOr(val32 + (size_t)img * 3 * groups * 256 + word, 1u << shift);
+}
+// what a device bin list needs from the fused pass: out[0] = some bin outside 0 < x < PW/2 (or a bad plane / index),
+// out[1] = largest row
+__global__ void __launch_bounds__(256) embed_bins_check(const uint32_t* __restrict__ bins, size_t nbits, SpecLayout lay, unsigned* out) {
+    unsigned bad = 0, ry = 0;
+    const uint32_t P = (uint32_t)min((size_t)lay.PH * lay.PW, (size_t)0x40000000u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbits; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t lin = bins[i] & 0x3FFFFFFFu;
+        const unsigned y = lin / (uint32_t)lay.PW, x = lin % (uint32_t)lay.PW;
+        bad |= ((bins[i] >> 30) > 2u || lin >= P || x == 0u || x >= (unsigned)(lay.PW >> 1)) ? 1u : 0u;
+        ry = max(ry, y);
+    }
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    ry = __reduce_max_sync(0xffffffffu, ry);
+    if ((threadIdx.x & 31) == 0) { if (bad) atomicMax(out, 1u); atomicMax(out + 1, ry); }
+}
+cudaError_t launch_embed_bins_check(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, unsigned* d_out2) {
+    cudaError_t e = cudaMemsetAsync(d_out2, 0, 2 * sizeof(unsigned), L.stream);
+    if (e != cudaSuccess || nbits == 0) return e;
+    const unsigned grid = (unsigned)std::min<size_t>((nbits + 255) / 256, 4 * (size_t)L.sm_count);
+    embed_bins_check<<<grid, 256, 0, L.stream>>>(bins, nbits, lay, d_out2);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+size_t embed_mask_bytes(int ld, int nplanes) { return (size_t)nplanes * (ld / 2) * 512 * sizeof(uint16_t); }
+cudaError_t launch_embed_pres(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, uint16_t* pres) {
+    cudaError_t e = cudaMemsetAsync(pres, 0, embed_mask_bytes(lay.ld, 3), L.stream);
+    if (e != cudaSuccess || nbits == 0) return e;
+    int lw = 0;
+    while ((1 << lw) < lay.PW) lw++;
+    embed_pres_build<<<(unsigned)((nbits + 255) / 256), 256, 0, L.stream>>>(bins, nbits, lw, lay.ld / 2, (uint32_t*)pres);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+cudaError_t launch_embed_val(const Launcher& L, const uint32_t* bins, const uint8_t* bits, size_t nbits, int nimg, SpecLayout lay, uint16_t* val) {
+    cudaError_t e = cudaMemsetAsync(val, 0, embed_mask_bytes(lay.ld, nimg * 3), L.stream);
+    if (e != cudaSuccess || nbits == 0 || nimg == 0) return e;
+    int lw = 0;
+    while ((1 << lw) < lay.PW) lw++;
+    embed_val_build<<<dim3((unsigned)((nbits + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(bins, bits, nbits, lw, lay.ld / 2, (uint32_t*)val);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+
+// S:1009-1012 for the speculative (column-resident) embed: an image over capacity leaves as its cover
+__global__ void __launch_bounds__(256) passthrough_over_capacity(const uint8_t* __restrict__ cover, uint8_t* __restrict__ stego, size_t img_bytes,
+                                                                 const uint64_t* __restrict__ usable, uint64_t nbits) {
+    const int img = blockIdx.y;
+    if (usable[img] >= nbits) return;
+    const uint8_t* src = cover + (size_t)img * img_bytes;
+    uint8_t* dst = stego + (size_t)img * img_bytes;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < img_bytes; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+cudaError_t launch_passthrough(const Launcher& L, const uint8_t* cover, uint8_t* stego, size_t img_bytes, int nimg, const uint64_t* usable, size_t nbits) {
+    if (nimg == 0 || nbits == 0) return cudaSuccess;
+    passthrough_over_capacity<<<dim3(64, (unsigned)nimg), 256, 0, L.stream>>>(cover, stego, img_bytes, usable, (uint64_t)nbits);
     TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }

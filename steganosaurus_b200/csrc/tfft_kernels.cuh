@@ -57,6 +57,18 @@ struct PassArgs {
     // signmap (sign_map_words() uint32 per plane, layout in tfft_pencil.cu); spec rows are NOT written.
     uint32_t* signmap;
     double sign_alpha;
+    // Column-resident embed (fused_embed = 1; axis 1, 4096-row half planes, in_rows = out_rows = H): forward column pass,
+    // phase write (write_bit_on_bin S:712-732) and inverse column pass in one shared-memory residency (pencil_col_embed_w in
+    // tfft_pencil.cu).  The spectrum is not stored; q = |F|^2 of every element leaves as two 32-bit planes qhi / qlo (the
+    // exact double, layout of q32) next to the sample.  embed_pres [3][ld/2][512] / embed_val [nplanes][ld/2][512]: per
+    // thread and column pair, bit k3 = a bin at row k1 + 16 m + 256 k3 / the bit to write there (embed_masks_* below).
+    int fused_embed;
+    const uint16_t* embed_pres;
+    const uint16_t* embed_val;
+    int embed_k3max;
+    double embed_cos, embed_sin;
+    uint32_t* qhi;
+    uint32_t* qlo;
 };
 // uint32 words per plane of the sign map of a 4096-row plane with `cols` stored columns
 inline size_t sign_map_words(int cols) { return (size_t)(cols / 2) * 16 * 8; }
@@ -112,7 +124,22 @@ void median_work_carve(MedianWork& w, void* base, int nplanes, uint32_t cand_cap
 // q32 != null (4096-row half planes): float copy of q = |F|^2 of every element left by the column pass (PassArgs::q32)
 cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int nplanes, SpecLayout lay,
                                    double magmin, double rlo, double rhi, MedianWork w,
-                                   double* d_median, uint64_t* d_usable, unsigned presampled = 0, const float* q32 = nullptr);
+                                   double* d_median, uint64_t* d_usable, unsigned presampled = 0, const float* q32 = nullptr,
+                                   const uint32_t* qhi = nullptr, const uint32_t* qlo = nullptr);
+// qhi / qlo != null (column-resident embed, 4096-row half planes, presampled > 0): the two 32-bit planes of q = |F|^2 the
+// fused pass left (PassArgs::qhi / qlo); spec is not read (it no longer holds the spectrum).  The selection then runs on
+// the bit patterns of q and the median is sqrt() of the selected element (within 1 ulp of hypot() of the same element).
+
+// ---- column-resident embed (pencil_col_embed_w): bin masks, bin-list check, capacity pass-through ------------------
+size_t embed_mask_bytes(int ld, int nplanes);  // bytes of a [nplanes][ld/2][512] uint16 mask array
+cudaError_t launch_embed_pres(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, uint16_t* pres /*[3][ld/2][512]*/);
+cudaError_t launch_embed_val(const Launcher& L, const uint32_t* bins, const uint8_t* bits, size_t nbits, int nimg, SpecLayout lay,
+                             uint16_t* val /*[nimg*3][ld/2][512]*/);
+// d_out2[0] = 1 when some bin is outside 0 < x < PW/2 (or invalid), d_out2[1] = largest row of the list
+cudaError_t launch_embed_bins_check(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, unsigned* d_out2);
+// stego[img] = cover[img] for every image with usable[img] < nbits (S:1009-1012)
+cudaError_t launch_passthrough(const Launcher& L, const uint8_t* cover, uint8_t* stego, size_t img_bytes, int nimg, const uint64_t* usable, size_t nbits);
+bool fused_embed_supported(const Launcher& L);  // PassArgs::fused_embed is available (TMA column kernels in use)
 
 // ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
 cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,

@@ -244,7 +244,8 @@ __device__ __forceinline__ double u8_to_double(unsigned v) {
 
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
-template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256>
+// TW_SHIFT: tw[m << TW_SHIFT] = w_N^m (the global table holds w_16384^k; a shared-memory copy of w_N^m, m < 256, has shift 0)
+template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256, int TW_SHIFT = TW_LOG2 - LOG2N>
 __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
                                        const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/) {
     using G = Geo<LOG2N, VEC>;
@@ -267,7 +268,7 @@ __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2*
             }
         }
         dft<S, G::R1>(x);
-        double2 w1 = tw[(size_t)m << (TW_LOG2 - LOG2N)];
+        double2 w1 = tw[(size_t)m << TW_SHIFT];
         if (S < 0) w1.y = -w1.y;
         twiddle<G::R1>(x, w1);
 #pragma unroll
@@ -730,6 +731,288 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
                 tma_commit();
             }
         }
+    }
+    if (tid == TS0 || tid == TS1) tma_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
+// Column-resident embed (N = 4096, two columns per CTA): forward column FFT -> median inputs -> phase write at this
+// pair's bins -> inverse column FFT, in ONE shared-memory residency.  Replaces the three-kernel sequence
+// pencil_col_tma_w<+1> -> embed_scatter -> pencil_col_tma_w<-1> (write_bit_on_bin S:712-732 between the column halves of
+// fft2d S:359-366 forward and inverse): the spectrum is never written to HBM, only
+//   * q = |F|^2 of every element as its exact double, split into two 32-bit planes (qhi: sign/exponent/20 mantissa
+//     bits, qlo: the other 32) in the warp order of the float copy above -- the median / capacity scan streams qhi (4 bytes
+//     per element) and fetches qlo only for the ~1 % of elements its bracket cannot decide on the top word,
+//   * the stratified median sample, and
+//   * rows < H of the inverse column transform, in place over the row pass's output.
+// Ownership makes the middle free: after the forward pass thread (k1, m, c) holds rows k1 + 16 m + 256 k3 (k3 = 0..15) of
+// column c -- exactly the sixteen stride-256 inputs of the inverse pass's first radix-16 butterfly at position
+// k1 + 16 m.  So the phase write happens on registers (the half-spectrum layout stores exactly one element per bin for
+// 0 < x < PW/2; the host refuses other lists for this path) and the inverse starts without an exchange.
+// Bins arrive as two 16-bit masks per thread and pair: pres (bit k3: a bin sits at my row block k3; shared by the batch,
+// the walk is cover-independent S:797-799) and val (the bit to write; per image).
+// Shared memory: L = 128 KB (TMA landing + forward exchange 1, free for the NEXT pair's loads as soon as the stage-2
+// inputs are in registers) and X = 80 KB (warp-private slices for the two warp-local exchanges and the store staging, and
+// -- between them, together with the tail of L -- the inverse's block-wide exchange 1, see XE_OFFSET).
+// The embed is speculative with respect to capacity (S:1009-1012 needs the median, which needs the whole spectrum): the
+// caller passes the cover through afterwards for images whose usable < nbits.
+// ------------------------------------------------------------------------------------------
+struct ColEmbedArgs {
+    const double2* tw;
+    long long nitems;      // nplanes * groups_per_plane
+    int groups_per_plane;  // ld / 2 column pairs
+    unsigned long long* sample_q;  // median sample (null: off), as pencil_col_tma_w
+    unsigned sample_stride;
+    int sample_groups;
+    uint32_t* qhi;         // [plane][g][k1][j][lane] uint4: top words of q for rows k1 + 16 m + 256 (4 j + 0..3), lane = 2 m + c
+    uint32_t* qlo;         // the low words, same layout
+    const uint16_t* pres;  // [plane % 3][g][tid]   bit k3: a bin at (row k1 + 16 m + 256 k3, column 2 g + c)
+    const uint16_t* val;   // [plane][g][tid]       the bits to write there
+    int k3max;             // largest row block that holds a bin
+    double cos_a, sin_a;   // of alpha (host libm: bit-exact with the reference's polar())
+};
+
+// Inverse exchange 1 (block-wide, 16-byte entries): entry p = k * 256 + position sits at row xe_pos(p) of a padded
+// [4352][2 columns] image (one pad row per 16: the stride-16 writers and the stride-1 readers are both conflict-free).
+// The image (136 KB) spans the last 56 KB of L -- row blocks 9..15, which no TMA load of a <= 2304-row input ever
+// lands in -- and the 80 KB of X behind it, so the next pair's loads can still be issued as early as in the unfused pass.
+constexpr int XE_ROWS = 4096 + 256;
+constexpr size_t XE_OFFSET = (size_t)9 * 256 * 2 * 16;                       // 72 KB into L
+constexpr size_t X_EMBED_BYTES = (size_t)XE_ROWS * 32 - ((size_t)131072 - XE_OFFSET);  // 80 KB
+__device__ __forceinline__ int xe_pos(int p) { return p + (p >> 4); }
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+template <int NZ, int K3N>
+__global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_constant__ CUtensorMap in_map,
+                                                             const __grid_constant__ CUtensorMap out_map,
+                                                             const __grid_constant__ CUtensorMap out_map2, ColEmbedArgs a) {
+    constexpr int LOG2N = 12, VEC = 2;
+    using G = Geo<LOG2N, VEC>;
+    constexpr int BOX_ROWS = 256, NBOX = G::N / BOX_ROWS;
+    static_assert(NZ >= 1 && NZ <= NBOX && K3N >= 1 && K3N <= 16, "block counts");
+    constexpr bool EARLY_PREFETCH = NZ <= 9;  // the landing area stays clear of the inverse exchange image
+    // Results leave through the warp slices of X, eight row blocks (64 KB) at a time.  One or two extra blocks (UHD: the
+    // ninth) are staged behind them in the 16 KB X has left, so both box stores of a pair are issued together; more than
+    // that waits for the first store to have read the slices (second round, as pencil_col_tma_w).
+    constexpr int K3B = K3N > 8 ? K3N - 8 : 0;        // row blocks beyond the first eight
+    constexpr bool ONE_ROUND = K3B <= 2;
+    constexpr int TL = 0, TS0 = 160, TS1 = 320;
+    constexpr int TLAST = (K3N > 8 && !ONE_ROUND) ? TS1 : TS0;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ uint64_t full_bar, lfree, xfree_a, xfree_b, staged0, staged1;
+    __shared__ __align__(16) double2 tw_s[256];       // w_4096^j, j < 256: every twiddle base of the three stages
+    __shared__ __align__(16) uint32_t s_pres[256], s_val[256];  // this pair's bin masks (two threads per word)
+    double2* L = (double2*)smem_raw;
+    double* X = (double*)(smem_raw + G::L_BYTES);
+    double2* X2 = (double2*)(smem_raw + G::L_BYTES + 65536);  // staging of the row blocks beyond the eighth (ONE_ROUND)
+    double2* XE = (double2*)(smem_raw + XE_OFFSET);
+    const int tid = threadIdx.x, c = tid & 1, tt = tid >> 1;
+    const int k1 = tt >> 4, m = tt & 15;
+    const int mp = k1 + 16 * m;                      // my position in the inverse pass's first stage (row mod 256)
+    double* Xw = X + (size_t)k1 * 256 * VEC;
+    double2* Sw = (double2*)Xw;
+    const double scale = 1.0 / (double)G::N;        // S:357
+
+    if (tid == 0) {
+        mbar_init(&full_bar, 1);
+        mbar_init(&lfree, 512);
+        mbar_init(&xfree_a, 1);
+        mbar_init(&xfree_b, 1);
+        mbar_init(&staged0, 512);
+        mbar_init(&staged1, 512);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (tid < 256) tw_s[tid] = a.tw[(size_t)tid << (TW_LOG2 - LOG2N)];
+    __syncthreads();
+
+    const int gpp = a.groups_per_plane;
+    auto issue_load = [&](int plane, int g) {
+        mbar_expect_tx(&full_bar, (unsigned)((size_t)NZ * BOX_ROWS * VEC * 16));
+#pragma unroll 1
+        for (int j = 0; j < NZ; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
+    };
+    // position of item = plane * gpp + g, advanced without divisions
+    int plane = (int)(blockIdx.x / (unsigned)gpp), g = (int)(blockIdx.x % (unsigned)gpp);
+    const int dplane = (int)(gridDim.x / (unsigned)gpp), dg = (int)(gridDim.x % (unsigned)gpp);
+    const long long stride = gridDim.x;
+    long long item = blockIdx.x;
+    if (tid == TL && item < a.nitems) issue_load(plane, g);
+    unsigned parity = 0;
+    for (; item < a.nitems; item += stride, parity ^= 1) {
+        int nplane = plane + dplane, ng = g + dg;
+        if (ng >= gpp) { ng -= gpp; nplane++; }
+        // this pair's bin masks: 4-byte async copies straight to shared memory (no registers held across the forward pass);
+        // completed before the barrier below, read at the phase write
+        if (a.pres) {
+            const uint32_t* src = tid < 256 ? (const uint32_t*)a.pres + ((size_t)(plane % 3) * gpp + g) * 256 + tid
+                                            : (const uint32_t*)a.val + ((size_t)plane * gpp + g) * 256 + (tid - 256);
+            cp_async4(tid < 256 ? &s_pres[tid] : &s_val[tid - 256], src);
+            cp_async_commit();
+        }
+        // ================= forward column transform (as pencil_col_tma_w<+1, NZ, 16>) =================
+        mbar_wait(&full_bar, parity);
+        stage1<+1, LOG2N, VEC, false, NZ, 0>(L, tt, c, tw_s, nullptr, 0, 0, -1);
+        cp_async_wait_all();
+        __syncthreads();
+        double2 x[16];
+        stage2_load<LOG2N, VEC>(L, tt, c, x);
+        mbar_arrive(&lfree);
+        if (tid == TLAST) {  // its own store of the previous pair's last half has finished reading X
+            tma_wait_read_all();
+            mbar_arrive(&xfree_a);
+        }
+        if (EARLY_PREFETCH && tid == TL && item + stride < a.nitems) {
+            mbar_wait(&lfree, parity);  // L is free
+            fence_async_proxy();
+            issue_load(nplane, ng);
+        }
+        dft<+1, 16>(x);
+        twiddle<16>(x, tw_s[16 * m]);  // w_256^m
+        double2 z[16];
+        mbar_wait(&xfree_a, parity);
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].x;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) z[n].x = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        __syncwarp();
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = x[oidx<16>(k2)].y;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        dft<+1, 16>(z);  // z[oidx(k3)] = F[row k1 + 16 m + 256 k3][column 2 g + c]
+        // ================= median inputs: q of every element (exact double, two word planes) + the sample =================
+        {
+            const size_t qbase = ((((size_t)plane * gpp + g) * 16 + k1) * 128 + (tid & 31)) * 4;  // in words
+            const bool samp = a.sample_q != nullptr && g < a.sample_groups && c == (g & 1);
+            const unsigned k3s = (((unsigned)tt * 2654435761u) >> 15 ^ ((unsigned)g * 0x9E3779B9u) >> 11 ^ (unsigned)plane * 7u) & 15u;
+            unsigned long long qs = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned hi[4], lo[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const double2 v = z[oidx<16>(4 * j + u)];
+                    const double q = fma(v.x, v.x, v.y * v.y);
+                    hi[u] = (unsigned)__double2hiint(q);
+                    lo[u] = (unsigned)__double2loint(q);
+                    if (k3s == (unsigned)(4 * j + u)) qs = (unsigned long long)__double_as_longlong(q);
+                }
+                *(uint4*)(a.qhi + qbase + (size_t)j * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *(uint4*)(a.qlo + qbase + (size_t)j * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (samp) a.sample_q[(size_t)plane * a.sample_stride + (size_t)g * 256 + tt] = qs;
+        }
+        // ================= phase write (write_bit_on_bin S:712-732) on the registers that own the bins =================
+        if (a.pres) {
+            const unsigned pres = (s_pres[tt] >> (16 * c)) & 0xFFFFu, val = s_val[tt] >> (16 * c);
+            if (__any_sync(0xffffffffu, pres != 0u)) {
+#pragma unroll
+                for (int k3 = 0; k3 < 16; k3++) {
+                    if (k3 > a.k3max) break;  // (uniform)
+                    if ((pres >> k3) & 1u) {
+                        double2& v = z[oidx<16>(k3)];
+                        // |F| (S:716).  sqrt of the correctly rounded sum of squares: within one ulp of abs(complex) and an order
+                        // of magnitude cheaper than hypot() under divergence; spectra here are far from over/underflow, and a
+                        // magnitude below 1e-154 ends at the 1e-12 floor either way
+                        const double mag = fmax(1e-12, sqrt(fma(v.x, v.x, v.y * v.y)));
+                        const double s = ((val >> k3) & 1u) ? a.sin_a : -a.sin_a;  // theta = +-alpha (S:718-720)
+                        v = make_double2(mag * a.cos_a, mag * s);          // std::polar(mag, theta); the mirror is not stored
+                    }
+                }
+            }
+        }
+        // ================= inverse column transform =================
+        // stage 1 in registers: inputs rows mp + 256 n = z[oidx(n)]
+        {
+#pragma unroll
+            for (int n = 0; n < 16; n++) x[n] = z[oidx<16>(n)];
+            dft<-1, 16>(x);
+            double2 w1 = tw_s[mp];
+            w1.y = -w1.y;
+            twiddle<16>(x, w1);  // x[oidx(k)] = exchange-1 entry k * 256 + mp
+        }
+        __syncthreads();  // every warp is past the reads of its private slice of X: the exchange image may cover it
+#pragma unroll
+        for (int k = 0; k < 16; k++) XE[xe_pos(k * 256 + mp) * VEC + c] = x[oidx<16>(k)];
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < 16; n++) z[n] = XE[xe_pos(k1 * 256 + n * 16 + m) * VEC + c];
+        __syncthreads();  // block-wide reads done: the slices of X are private again, L's tail is free
+        if (!EARLY_PREFETCH && tid == TL && item + stride < a.nitems) {  // (all 16 landing blocks overlap the image)
+            fence_async_proxy();
+            issue_load(nplane, ng);
+        }
+        // stage 2, warp-local transpose, stage 3 (as pencil_col_tma_w<-1>)
+        dft<-1, 16>(z);
+        {
+            double2 w2 = tw_s[16 * m];
+            w2.y = -w2.y;
+            twiddle<16>(z, w2);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = z[oidx<16>(k2)].x;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) x[n].x = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        __syncwarp();
+#pragma unroll
+        for (int k2 = 0; k2 < 16; k2++) Xw[((k2 << 4) | (m ^ k2)) * VEC + c] = z[oidx<16>(k2)].y;
+        __syncwarp();
+#pragma unroll
+        for (int n = 0; n < 16; n++) x[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
+        dft<-1, 16>(x);  // x[oidx(k3)] = output row k1 + 16 m + 256 k3 of column c
+        // ---- first half of the results: rows with k3 < 8 (and, ONE_ROUND, the one or two blocks behind them)
+        __syncwarp();
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) {
+            if (k3 >= K3N) continue;
+            double2 v = x[oidx<16>(k3)];
+            v.x *= scale; v.y *= scale;
+            Sw[(k3 * 16 + m) * VEC + c] = v;
+        }
+        if constexpr (K3N > 8 && ONE_ROUND) {
+#pragma unroll
+            for (int k3 = 8; k3 < K3N; k3++) {
+                double2 v = x[oidx<16>(k3)];
+                v.x *= scale; v.y *= scale;
+                X2[((k1 * K3B + (k3 - 8)) * 16 + m) * VEC + c] = v;  // image [k1][k3 - 8][k2][column] of the second box
+            }
+        }
+        fence_async_proxy();
+        mbar_arrive(&staged0);
+        if (tid == TS0) {
+            mbar_wait(&staged0, parity);
+            tma_store_5d(&out_map, X, g * VEC * 2, 0, 0, 0, plane);
+            if constexpr (K3N > 8 && ONE_ROUND) tma_store_5d(&out_map2, X2, g * VEC * 2, 0, 8, 0, plane);
+            tma_commit();
+            if constexpr (K3N > 8 && !ONE_ROUND) {
+                tma_wait_read_all();
+                mbar_arrive(&xfree_b);
+            }
+        }
+        if constexpr (K3N > 8 && !ONE_ROUND) {
+            mbar_wait(&xfree_b, parity);
+#pragma unroll
+            for (int k3 = 8; k3 < 16; k3++) {
+                if (k3 >= K3N) continue;
+                double2 v = x[oidx<16>(k3)];
+                v.x *= scale; v.y *= scale;
+                Sw[((k3 - 8) * 16 + m) * VEC + c] = v;
+            }
+            fence_async_proxy();
+            mbar_arrive(&staged1);
+            if (tid == TS1) {
+                mbar_wait(&staged1, parity);
+                tma_store_5d(&out_map, X, g * VEC * 2, 0, 8, 0, plane);
+                tma_commit();
+            }
+        }
+        plane = nplane; g = ng;
     }
     if (tid == TS0 || tid == TS1) tma_wait_all();
 }
@@ -1362,7 +1645,7 @@ bool make_col_map(CUtensorMap* m, const double2* spec, int nplanes, int PH, int 
 
 // store map of pencil_col_tma_w (N = 4096, VEC = 2): dims (fastest first) column doubles, k2, k3, k1, plane with
 // row = k1 + 16 k2 + 256 k3; the k3 extent clips the rows that are not needed (multiples of 256 rows)
-bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int PH, int PW, int out_rows) {
+bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int PH, int PW, int out_rows, int k3box = 8) {
     EncodeTiledFn enc = get_encoder();
     if (!enc) return false;
     const cuuint64_t rowb = (cuuint64_t)PW * 16;
@@ -1371,7 +1654,7 @@ bool make_col_store_map5(CUtensorMap* m, const double2* spec, int nplanes, int P
     if (k3n < 1) k3n = 1;
     cuuint64_t dims[5] = {(cuuint64_t)2 * PW, 16, (cuuint64_t)k3n, 16, (cuuint64_t)nplanes};
     cuuint64_t strides[4] = {16 * rowb, 256 * rowb, rowb, (cuuint64_t)PH * rowb};
-    cuuint32_t box[5] = {4, 16, 8, 16, 1};
+    cuuint32_t box[5] = {4, 16, (cuuint32_t)k3box, 16, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, (void*)spec, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1404,6 +1687,30 @@ cudaError_t run_col_tma_w(const Launcher& L, const PassArgs& p, bool* ok) {
     cudaError_t e = set_smem(kern, smem);
     if (e != cudaSuccess) return e;
     kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, a);
+    if (L.launch_counter) ++*L.launch_counter;
+    return cudaGetLastError();
+}
+
+template <int NZ, int K3N>
+cudaError_t run_col_embed_w(const Launcher& L, const PassArgs& p, bool* ok) {
+    using G = pk::Geo<12, 2>;
+    CUtensorMap in_map, out_map, out_map2;
+    constexpr int K3B = K3N > 8 ? K3N - 8 : 0;
+    *ok = make_col_map(&in_map, p.spec, p.nplanes, p.PH, p.PW, p.in_rows, 2) &&
+          make_col_store_map5(&out_map, p.spec, p.nplanes, p.PH, p.PW, p.out_rows) &&
+          make_col_store_map5(&out_map2, p.spec, p.nplanes, p.PH, p.PW, p.out_rows, (K3B >= 1 && K3B <= 2) ? K3B : 8);
+    if (!*ok) return cudaSuccess;
+    pk::ColEmbedArgs a;
+    a.tw = p.tw; a.groups_per_plane = p.PW / 2; a.nitems = (long long)p.nplanes * a.groups_per_plane;
+    a.sample_q = p.sample_q; a.sample_stride = p.sample_stride;
+    a.sample_groups = (int)(p.sample_stride ? (p.PW - 16) / 2 : 0);  // p.PW is ld = PW_full/2 + 16: pairs below the Nyquist column
+    a.qhi = p.qhi; a.qlo = p.qlo; a.pres = p.embed_pres; a.val = p.embed_val; a.k3max = p.embed_k3max;
+    a.cos_a = p.embed_cos; a.sin_a = p.embed_sin;
+    const size_t smem = G::L_BYTES + pk::X_EMBED_BYTES;
+    auto kern = pk::pencil_col_embed_w<NZ, K3N>;
+    cudaError_t e = set_smem(kern, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid_for(L, a.nitems, 1), 512, smem, L.stream>>>(in_map, out_map, out_map2, a);
     if (L.launch_counter) ++*L.launch_counter;
     return cudaGetLastError();
 }
@@ -1506,6 +1813,13 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
                          : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
     if constexpr (LOG2N == 12) {  // warp-local exchange + permuting store (TFFT_COL_KERNEL=block keeps the 9-barrier kernel)
         static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
+        if (p.fused_embed) {  // forward + phase write + inverse in one residency (the caller checked fused_embed_supported)
+            if (L.fft_impl != 1 || blockk || !p.qhi || !p.qlo || p.PW < 2 || p.in_rows != p.out_rows) return cudaErrorNotSupported;
+            bool ok = false;
+            // (a 4096-row plane has more than 2048 image rows: 9 row blocks for UHD, else all 16)
+            cudaError_t e = p.in_rows <= 9 * 256 ? run_col_embed_w<9, 9>(L, p, &ok) : run_col_embed_w<16, 16>(L, p, &ok);
+            return (e == cudaSuccess && !ok) ? cudaErrorNotSupported : e;
+        }
         if (p.signmap) {  // extract without jitter: the pass only leaves the read bits behind (the caller checked signmap_supported)
             if (L.fft_impl != 1 || blockk || p.inverse || p.out_rows > 8 * 256 || p.PW < 2) return cudaErrorNotSupported;
             bool ok = false;
@@ -1539,9 +1853,11 @@ bool signmap_supported(const Launcher& L) {
     return L.fft_impl == 1 && !blockk && get_encoder() != nullptr;
 }
 
+bool fused_embed_supported(const Launcher& L) { return signmap_supported(L); }
+
 cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* handled) {
     *handled = true;
-    if (p.signmap && !(p.log2n == 12 && p.axis == 1)) return cudaErrorNotSupported;
+    if ((p.signmap || p.fused_embed) && !(p.log2n == 12 && p.axis == 1)) return cudaErrorNotSupported;
     // the fused u8 passes need W <= PW == N (always true) and run along x only
     switch (p.log2n) {
         case 12: return dispatch<12>(L, p);

@@ -261,7 +261,7 @@ def test_median_exact_many_planes(ctx):
         for p in range(3):
             mags = np.hypot(F[p].real, F[p].imag).ravel()
             want = np.partition(mags, mags.size // 2)[mags.size // 2]
-            assert abs(med[i, p] - want) <= 4e-16 * want, (i, p, med[i, p], want)
+            assert abs(med[i, p] - want) <= 1e-15 * want, (i, p, med[i, p], want)  # (4096-row planes: sqrt of the q order statistic)
 
 
 @pytest.mark.parametrize("W,H,n", [(700, 3000, 3), (4096, 4096, 1), (3840, 2160, 2), (512, 2100, 4)])
@@ -277,7 +277,7 @@ def test_median_4096_rows(ctx, W, H, n):
         for p in range(3):
             mags = np.hypot(F[p].real, F[p].imag).ravel()
             want = np.partition(mags, mags.size // 2)[mags.size // 2]
-            assert abs(med[i, p] - want) <= 4e-16 * want, (i, p, med[i, p], want)
+            assert abs(med[i, p] - want) <= 1e-15 * want, (i, p, med[i, p], want)  # (4096-row planes: sqrt of the q order statistic)
         if i == 0:
             Fo = o.forward_spectrum(imgs[i])
             wus = sum(o.count_plane(Fo[p], 0.05, 0.45, 0.01 * o.median_abs(Fo[p])) for p in range(3))
