@@ -122,8 +122,9 @@ def make_covers(batch: int, W: int, H: int, distinct: int = 8) -> np.ndarray:
 _CPU_STATE = None
 
 
-def _cpu_init(W, H, payload, use_ref):
-    """Pool initializer: every worker process builds its own image, bin list and frame once."""
+def _cpu_init(W, H, payload, use_ref, mode="embed+extract"):
+    """Pool initializer: every worker process builds its own image, bin list and frame once (mode "extract": also the
+    stego image the timed extract reads, made by the same checker outside the timed region)."""
     global _CPU_STATE
     sys.path.insert(0, ROOT)
     from oracle import pyoracle as O
@@ -135,7 +136,9 @@ def _cpu_init(W, H, payload, use_ref):
     from steganosaurus_b200 import host
     bins = host.walk(b"correct horse battery staple", PH, PW, nbits, PARAMS["rmin"], PARAMS["rmax"], 0.7)[0]
     bits = make_frame_bits(1, payload, 2000 + idx)[0]
-    _CPU_STATE = (O.ref() if use_ref else O.port(), cover, bins, bits)
+    o = O.ref() if use_ref else O.port()
+    stego = o.embed(cover, bins, bits, PARAMS["alpha"], PARAMS["center"], PARAMS["magmin"], PARAMS["rmin"], PARAMS["rmax"])["stego"] if mode == "extract" else None
+    _CPU_STATE = (o, cover, bins, bits, mode, stego)
 
 
 def _cpu_ready(_):
@@ -144,8 +147,14 @@ def _cpu_ready(_):
 
 
 def _cpu_step(_):
-    o, cover, bins, bits = _CPU_STATE
+    o, cover, bins, bits, mode, stego = _CPU_STATE
     t0 = time.time()
+    if mode == "extract":  # forward FFT + phase read + Rep-3 / Rep-7 vote of one stego image (S:1116-1268)
+        if o.kind == "reference":
+            o.time_extract(stego, bins, PARAMS["alpha"], PARAMS["center"])
+        else:
+            o.extract(stego, bins[:912], 3, PARAMS["alpha"], PARAMS["center"])
+        return t0, time.time(), 0.0, 0.0
     if o.kind == "reference":
         te, stego = o.time_embed(cover, bins, bits, PARAMS["alpha"], PARAMS["center"], PARAMS["magmin"], PARAMS["rmin"], PARAMS["rmax"])
         tx, _ = o.time_extract(stego, bins, PARAMS["alpha"], PARAMS["center"])
@@ -157,7 +166,7 @@ def _cpu_step(_):
 
 
 class CpuArm:
-    def __init__(self, W, H, payload, workers=None):
+    def __init__(self, W, H, payload, workers=None, mode="embed+extract"):
         import multiprocessing as mp
         from oracle import pyoracle as O
         self.use_ref = O.have_ref()
@@ -170,8 +179,8 @@ class CpuArm:
         PH, PW = 1 << (H - 1).bit_length(), 1 << (W - 1).bit_length()
         per = 140 * PH * PW  # reference needs ~130 B per padded bin
         self.workers = max(1, min(ncpu, int(avail * 0.7 // per))) if workers is None else workers
-        self.W, self.H, self.payload = W, H, payload
-        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init, initargs=(W, H, payload, self.use_ref))
+        self.W, self.H, self.payload, self.mode = W, H, payload, mode
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_cpu_init, initargs=(W, H, payload, self.use_ref, mode))
         self.pool.map(_cpu_ready, range(self.workers), chunksize=1)  # wait until every worker is initialised
 
     def step(self):
@@ -186,20 +195,26 @@ class CpuArm:
     def describe(self, value):
         return {"value": value, "unit": UNIT, "cores": self.workers, "kind": self.kind,
                 "sample": f"{self.workers} concurrent single-threaded processes x 1 image {self.W}x{self.H} "
-                          f"({self.payload}-byte frame) embed+extract per step; hot-path stages only "
+                          f"({self.payload}-byte frame) {self.mode} per step; hot-path stages only "
                           f"(to_planes..from_planes incl. median, capacity, F3 copy; PNG, KDF, walk excluded)"}
+
+
+def cpu_measure(arm, warmup, steps):
+    """Mean wall seconds of one CPU step after `warmup` untimed ones (both arms of bench.py use this)."""
+    for _ in range(warmup):
+        arm.step()
+    return float(np.mean([arm.step() for _ in range(steps)]))
 
 
 def run_reference_arm(args):
     rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
+    if args.config == "c4":
+        return run_c4_reference(args)
     arm = CpuArm(args.width, args.height, args.payload)
-    for _ in range(args.warmup):
-        arm.step()
-    ts = [arm.step() for _ in range(args.steps)]
+    t = cpu_measure(arm, args.warmup, args.steps)
     arm.close()
-    t = float(np.mean(ts))
     mp_per_step = arm.workers * args.width * args.height / 1e6
     value = mp_per_step / t
     line = {
@@ -216,8 +231,149 @@ def run_reference_arm(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE config 4: extract-only throughput sweep 512^2 -> 8192^2 over synthetic stego batches (forward FFT + phase
+# gather + Rep-3 / Rep-7 decode).  One JSON line per N.  SURVEY 8(d): batch = max(8, floor(8 GiB / (48 N^2))) capped at
+# 256, payload = 50 % of the embed capacity, real keyed turtlewalk; stego batches are made by our embed (validated against
+# the reference in tests/test_configs.py).
+C4_METRIC = "extract-only megapixels/sec (synthetic stego batch, forward FFT + phase gather + Rep-3/Rep-7 decode)"
+C4_CPU_MAX_N = 4096  # one 8192^2 reference extract is ~60 s of CPU time per image: not sampled
+
+
+def c4_case(ctx, N):
+    from steganosaurus_b200 import host, synth
+    batch = min(256, max(8, int((8 << 30) // (48 * N * N))))
+    cover1 = synth.gen_cover(N, N, 7)
+    _, usable, _ = ctx.embed_batch(cover1[None], np.zeros(0, np.uint32), np.zeros((1, 0), np.uint8))
+    cap = int(usable[0])
+    plen = max(16, (cap // 2 - 912) // 56 - 16)
+    nbits = synth.frame_len(plen)
+    bins = host.walk(b"correct horse battery staple", N, N, nbits, PARAMS["rmin"], PARAMS["rmax"], 0.7)[0]
+    bits1 = make_frame_bits(1, plen, N)[0]
+    distinct = min(batch, 4)
+    covers = np.stack([synth.gen_cover(N, N, 7 + i) for i in range(distinct)])
+    stego, _, _ = ctx.embed_batch(covers, bins, np.stack([bits1] * distinct))
+    return batch, plen, nbits, cap, bins, bits1, np.stack([stego[i % distinct] for i in range(batch)])
+
+
+def run_c4(args):
+    import torch
+    import steganosaurus_b200 as sb
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    from steganosaurus_b200 import shard
+    timing = shard.Timing(dist, dev)
+    peak, peak_src = measured_peak_hbm()
+    ctx = sb.Context(local_rank)
+    for N in [int(x) for x in args.sizes.split(",")]:
+        cpu_base = None
+        batch, plen, nbits, cap, bins, bits1, stego = c4_case(ctx, N)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and N <= C4_CPU_MAX_N:
+            arm = CpuArm(N, N, plen, mode="extract")
+            t = cpu_measure(arm, 1, 1)
+            arm.close()
+            cpu_base = arm.describe(arm.workers * N * N / 1e6 / t)
+        d_stego = torch.from_numpy(stego).to(dev)
+        d_bins = torch.from_numpy(bins.view(np.int32)).to(dev)
+        d_hdr = torch.zeros(batch, 38, dtype=torch.uint8, device=dev)
+        d_pay = torch.zeros(batch, plen + 16, dtype=torch.uint8, device=dev)
+
+        def step_dev():
+            ctx.extract_frame_dev(d_stego, d_bins, 912, d_hdr, d_pay, alpha=PARAMS["alpha"], center=PARAMS["center"])
+
+        for _ in range(args.warmup):
+            step_dev()
+        timing.barrier(); torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        ctx.profile_reset(); ctx.profile_enable(True)
+        l0 = ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_dev()
+        e1.record()
+        timing.barrier(); torch.cuda.synchronize()
+        dev_ms = timing.max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        launches = ctx.launches - l0
+        prof = ctx.profile_read(); ctx.profile_enable(False)
+        clocks = sampler.stop() if rank == 0 else None
+        want_hdr = np.packbits(bits1[:912:3]); want_pay = np.packbits(bits1[912::7])
+        wrong = int(np.unpackbits(d_hdr[0].cpu().numpy() ^ want_hdr).sum() + np.unpackbits(d_pay[0].cpu().numpy() ^ want_pay).sum())
+        # end to end: pinned host stego -> C-ABI (H2D inside) -> decoded bytes on the host
+        hs = torch.from_numpy(stego).pin_memory().numpy()
+        for _ in range(min(args.warmup, 2)):
+            ctx.extract_frame(hs, bins, 912, alpha=PARAMS["alpha"], center=PARAMS["center"])
+        timing.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.extract_frame(hs, bins, 912, alpha=PARAMS["alpha"], center=PARAMS["center"])
+        torch.cuda.synchronize()
+        e2e_ms = timing.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        if rank == 0:
+            name, (groups, ms, nbytes) = max(prof.items(), key=lambda kv: kv[1][1])
+            ach = (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0
+            mp = batch * N * N / 1e6
+            line = {
+                "metric": C4_METRIC, "value": world * mp / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"C4 extract-only: batch of {batch} {N}x{N} RGB stego images per GPU, {plen}-byte payload = 50 % of the "
+                                       f"capacity ({nbits} of {cap} bits, keyed turtlewalk), header + payload in one call",
+                           "N": N, "images_per_gpu_per_step": batch, "wrong_voted_bits_image0": wrong,
+                           "l2": "batch larger than L2" if batch * N * N * 3 > (126 << 20) else "batch smaller than L2: rotated over steps"},
+                "clocks": clocks,
+                "e2e": {"value": world * mp / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(batch * N * N * 3 + 4 * nbits), "d2h_bytes_per_step": int(batch * (38 + plen + 16)), "steps": args.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                             "traffic": None, "peak_source": peak_src, "launch_groups": groups,
+                             "kernels": {k: {"groups": v[0], "ms": round(v[1], 3), "GBps": round((v[2] / 1e9) / (v[1] / 1e3), 1) if v[1] > 0 else None}
+                                         for k, v in prof.items() if v[0]}},
+                "cpu_baseline": cpu_base,
+            }
+            print(json.dumps(line), flush=True)
+        del d_stego, hs, stego
+        torch.cuda.empty_cache()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_c4_reference(args):
+    """--impl reference --config c4: the reference's own extract on the host cores, one line per N (bounded sample)."""
+    from steganosaurus_b200 import synth
+    for N in [int(x) for x in args.sizes.split(",")]:
+        if N > C4_CPU_MAX_N:
+            print(json.dumps({"impl": "reference", "metric": C4_METRIC, "config": {"N": N}, "unavailable": "one image is ~60 s of CPU time"}), flush=True)
+            continue
+        # same payload rule as the GPU arm, from the capacity SURVEY 6.2 quotes for this kind of cover (~0.2355 N^2 bits)
+        plen = max(16, (int(0.2355 * N * N) // 2 - 912) // 56 - 16)
+        arm = CpuArm(N, N, plen, mode="extract")
+        t = cpu_measure(arm, args.warmup, args.steps)
+        arm.close()
+        value = arm.workers * N * N / 1e6 / t
+        print(json.dumps({"impl": "reference", "metric": C4_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": {"workload": f"C4 extract-only {N}x{N}, {plen}-byte payload; CPU step = {arm.workers} images", "N": N},
+                          "cpu_baseline": arm.describe(value),
+                          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    if args.config == "c4":
+        return run_c4(args)
     import torch
     import steganosaurus_b200 as sb
     from steganosaurus_b200 import synth
@@ -245,7 +401,7 @@ def run_ours(args):
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         arm = CpuArm(W, H, args.payload)
-        t = arm.step()
+        t = cpu_measure(arm, 1, 1)  # one warm-up step, one timed step (~14 s each): the reference arm's code path
         arm.close()
         cpu_base = arm.describe(arm.workers * W * H / 1e6 / t)
 
@@ -394,6 +550,9 @@ def main():
     ap.add_argument("--width", type=int, default=W_UHD)
     ap.add_argument("--height", type=int, default=H_UHD)
     ap.add_argument("--payload", type=int, default=PAYLOAD)
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"],
+                    help="c3 (default): BASELINE's headline, the 4K UHD embed+extract batch; c4: extract-only sweep, one line per N")
+    ap.add_argument("--sizes", default="512,1024,2048,4096,8192", help="--config c4: the N of the N x N stego batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg (the line then has no e2e)")
     args = ap.parse_args()

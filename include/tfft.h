@@ -19,17 +19,24 @@
  *   memory   the caller owns every buffer passed in; the library owns its device workspace
  *
  * Entry points ending in _dev take DEVICE pointers and a cudaStream_t (as void*), enqueue
- * their work on that stream and return without synchronising.  The others take HOST
+ * their work on that stream and return without waiting for it (they may synchronise that stream ONCE at entry to
+ * look at the device bin list).  They return TFFT_OK once everything is enqueued: the capacity verdict of an embed
+ * is NOT in the return code -- pass d_usable and compare it with nbits after synchronising (images over capacity
+ * leave as their covers).  Device bin lists are trusted: a plane above 2 or an index outside the padded plane is
+ * the caller's bug, as with any device pointer.  One context works on ONE stream at a time (its workspaces are
+ * shared): synchronise, or order the streams with an event, before passing a different one.  The others take HOST
  * pointers (pinned memory from tfft_host_alloc recommended), copy in/out on internal
  * streams and are synchronous at return.
  *
- * Environment switches (read once; the defaults are the fast paths and none changes a result beyond
- * rounding): TFFT_FFT_IMPL=v0|lsu (baseline shared-memory kernel / cp.async column kernel),
- * TFFT_SPECTRUM=full (no Hermitian halving), TFFT_WIDE=0 (8192-pixel rows and tall images on the
- * unfused four-step path), TFFT_COL_SAMPLE=0 (median sample by a separate gather pass),
- * TFFT_EXTRACT_WINDOW=0 (extract transforms every column and keeps every row), TFFT_SIGNMAP=0 (extract
- * keeps spectra instead of read bits), TFFT_SCAN_Q32=0 (median scan reads the spectrum, not a float copy of |F|^2), TFFT_COL_KERNEL=block, TFFT_HOST_CHUNK / TFFT_HOST_SLOTS (host pipeline:
- * images per chunk, chunks in flight), TFFT_PINGPONG=1, TFFT_ROW_UNITS=1, TFFT_SCAN_CTAS (experiments).
+ * Environment switches (read once at tfft_create; the defaults are the fast paths, none changes a result beyond
+ * rounding, and every one has a parity test in tests/test_env_variants.py):
+ *   TFFT_FFT_IMPL=v0        every FFT pass on the simple shared-memory radix-2 kernel (cross-check of the pencil kernels)
+ *   TFFT_SPECTRUM=full      no Hermitian halving: full PH x PW spectra
+ *   TFFT_WIDE=0             8192-pixel rows and tall images on the unfused four-step path
+ *   TFFT_FUSED_EMBED=0      embed: forward columns -> embed_scatter -> inverse columns instead of the column-resident pass
+ *   TFFT_EXTRACT_WINDOW=0   extract transforms every column and keeps every row
+ *   TFFT_SIGNMAP=0          extract keeps spectra instead of read bits
+ *   TFFT_HOST_CHUNK, TFFT_HOST_SLOTS   host pipeline of the host-buffer entry points: images per chunk, chunks in flight
  */
 #ifndef TFFT_H
 #define TFFT_H
@@ -67,6 +74,12 @@ const char* tfft_strerror(int code);
 const char* tfft_last_cuda_error(const tfft_ctx* ctx);
 /* Upper bound for the spectrum workspace in bytes (default: 40% of device memory). */
 int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes);
+/* Params.adaptive_alpha (S:379, S:704-710; experimental and off by default upstream): when on, every later embed writes
+ * and every later extract reads bin (y,x) of plane p with alpha * clamp(|F[y][x]| / median_p, 0.5, 2) instead of alpha,
+ * exactly as write_bit_on_bin / read_bit_from_bin do with adaptive_alpha = true (the embed uses the cover's medians,
+ * the extract the stego image's own, S:922 / S:1124).  These calls run on the general path: no fused embed, no bin
+ * window, no sign map. */
+int tfft_set_adaptive_alpha(tfft_ctx* ctx, int on);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* tfft_host_alloc(size_t bytes);
 void tfft_host_free(void* p);

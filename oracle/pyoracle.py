@@ -179,11 +179,16 @@ class _Ref:
         L.ref_frame_bits.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_uint32, C.c_char_p, C.c_size_t,
                                      _u8p, _u8p]
         L.ref_frame_bits.restype = C.c_size_t
+        L.ref_set_adaptive.argtypes = [C.c_int]
         L.ref_time_embed_hotpath.argtypes = [_u8p, C.c_int, C.c_int, _u32p, _u8p, C.c_size_t, C.c_double, C.c_int,
                                              C.c_double, C.c_double, C.c_double, _u8p]
         L.ref_time_embed_hotpath.restype = C.c_double
         L.ref_time_extract_hotpath.argtypes = [_u8p, C.c_int, C.c_int, _u32p, C.c_size_t, C.c_double, C.c_int, _u8p]
         L.ref_time_extract_hotpath.restype = C.c_double
+
+    def set_adaptive(self, on: bool):
+        """--adaptive_alpha (S:704-710): subsequent embed / extract calls scale alpha by |F| / median, clamped to [0.5, 2]."""
+        self.L.ref_set_adaptive(int(on))
 
     # ---- hot path
     def fft1d(self, a, inverse=False):

@@ -111,6 +111,11 @@ uint64_t ref_count_plane(const double* f, int PH, int PW, double rmin, double rm
 // The whole embed hot path (S:912-923, S:997-1008, S:1086, S:1100-1103) for given bins/bits.
 // bins: plane<<30 | y*PW+x.  jitter must be 0 (KS::jitter(0) returns +-0).
 // Optional outputs (may be NULL): medians[3], usable, spectrum_after [3][PH][PW][2].
+// --adaptive_alpha (S:704-710, experimental upstream): when set, ref_embed / ref_extract_raw pass adaptive_alpha = true
+// and the per-plane medians to write_bit_on_bin / read_bit_from_bin exactly as do_embed / do_extract do
+static bool g_adaptive = false;
+void ref_set_adaptive(int on) { g_adaptive = on != 0; }
+
 void ref_embed(const uint8_t* cover, int W, int H, const uint32_t* bins, const uint8_t* bits,
                size_t nbits, double alpha, int center, double magmin, double rmin, double rmax,
                uint8_t* stego, double* medians, uint64_t* usable, double* spectrum_after) {
@@ -134,7 +139,7 @@ void ref_embed(const uint8_t* cover, int W, int H, const uint32_t* bins, const u
     for (size_t i = 0; i < nbits; i++) {
         int p, y, x;
         unpack_bin(bins[i], PW, p, y, x);
-        write_bit_on_bin(F[p], y, x, bits[i], alpha, 0.0, dummy, med[p], false);
+        write_bit_on_bin(F[p], y, x, bits[i], alpha, 0.0, dummy, med[p], g_adaptive);
     }
     if (spectrum_after)
         for (int p = 0; p < 3; p++) plane_to_flat(F[p], spectrum_after + (size_t)p * PH * PW * 2);
@@ -154,10 +159,12 @@ void ref_extract_raw(const uint8_t* stego, int W, int H, const uint32_t* bins, s
     int PW, PH;
     Plane F[3];
     forward3(stego, W, H, center != 0, PW, PH, F);
+    double med[3] = {1.0, 1.0, 1.0};
+    if (g_adaptive) for (int p = 0; p < 3; p++) med[p] = median_abs(F[p]);  // S:1124
     for (size_t i = 0; i < nbins; i++) {
         int p, y, x;
         unpack_bin(bins[i], PW, p, y, x);
-        raw_bits[i] = (uint8_t)read_bit_from_bin(F[p], y, x, alpha, 0.0, 1.0, false);
+        raw_bits[i] = (uint8_t)read_bit_from_bin(F[p], y, x, alpha, 0.0, med[p], g_adaptive);
     }
 }
 // Single-bin read (tie behaviour, S:734-746).

@@ -96,6 +96,10 @@ class Context:
     def launches(self) -> int:
         return int(self.L.tfft_launch_count(self.h))
 
+    def set_adaptive_alpha(self, on: bool):
+        """Params.adaptive_alpha (S:379, S:704-710): alpha scaled by |F| / median per bin in later embeds / extracts."""
+        self._check(self.L.tfft_set_adaptive_alpha(self.h, int(on)))
+
     def set_workspace_limit(self, nbytes: int):
         self._check(self.L.tfft_set_workspace_limit(self.h, nbytes))
 

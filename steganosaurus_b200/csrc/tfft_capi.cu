@@ -52,14 +52,15 @@ struct tfft_ctx {
     uint64_t launches = 0;
     int fft_impl = 1;
     bool use_half = true;   // real-input symmetry (half-spectrum workspace); TFFT_SPECTRUM=full disables
-    bool col_sample = true; // median sample dropped by the forward column pass (TFFT_COL_SAMPLE=0: separate gather kernel)
+    bool col_sample = true; // 4096-row half planes: the median sample is dropped by the forward column pass
     bool use_wide = true;   // 8192-pixel rows on the half-spectrum path; TFFT_WIDE=0 keeps them on the unfused four-step path
     bool use_window = true; // extract: the forward column pass keeps only the rows / columns that hold bins (TFFT_EXTRACT_WINDOW=0: all)
-    bool use_q32 = true;     // embed, 4096-row half planes: the median scan reads a float copy of |F|^2 (TFFT_SCAN_Q32=0: the spectrum)
+    bool use_q32 = true;     // embed, 4096-row half planes (unfused column stage): the median scan reads a float copy of |F|^2
     bool use_signmap = true; // extract without jitter, 4096-row planes: the column pass leaves read bits, not spectra (TFFT_SIGNMAP=0)
     bool use_fused = true;   // embed, 4096-row half planes, no jitter: forward columns + phase write + inverse columns in ONE pass
                              // (TFFT_FUSED_EMBED=0: the three-kernel sequence col_fwd -> embed_scatter -> col_inv)
     DevBuf pres;             // ... its per-call bin-presence masks [3][ld/2][512] (shared by the batch)
+    bool adaptive = false;   // tfft_set_adaptive_alpha: alpha scaled by |F| / median per bin (S:704-710; experimental upstream)
     unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
     unsigned* h_win = nullptr;  // ... and read back through this pinned pair
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
@@ -408,7 +409,7 @@ int embed_chunk_fused(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* 
 
 // can this call's column stage run fused?  (geometry part; the bin list part is decided by the callers)
 bool fused_geometry_ok(const tfft_ctx* ctx, const Launcher& L, const Geom& g, const double* jitter) {
-    return ctx->use_fused && ctx->col_sample && !jitter && !g.large && !g.col4 && g.half && g.lh == 12 && ctx->fft_impl == 1 &&
+    return ctx->use_fused && !ctx->adaptive && ctx->col_sample && !jitter && !g.large && !g.col4 && g.half && g.lh == 12 && ctx->fft_impl == 1 &&
            fused_embed_supported(L) && col_pass_samples(g.PH, g.PW, g.half) <= cand_cap_for(g.P);
 }
 
@@ -441,7 +442,8 @@ int embed_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_cove
     { ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * (q32 ? 4.0 : 16.0) * (double)g.E);
       CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), magmin, rmin * m, rmax * m, mw, d_median, d_usable, presampled, q32 ? (const float*)S.q32.p : nullptr)); }
     { ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nimg * (double)nbits * (16.0 + (g.half ? 16.0 : 32.0) + 5.0));
-      CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable)); }
+      CK(launch_embed(L, spec, nimg, g.lay(), d_bins, d_bits, nbits, d_jitter, alpha, cos(alpha), sin(alpha), d_usable,
+                      ctx->adaptive ? d_median : nullptr)); }
     return inverse_images(ctx, L, spec, other, d_stego, nimg, g, center);
 }
 
@@ -455,15 +457,24 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
     // Without jitter the read decision is a property of the element alone, so a 4096-row column pass can leave one bit
     // per element instead of 16 bytes (window of at most 2048 rows, no bin behind the Nyquist column, alpha away from
     // 0 and pi so that the decision is the sign of the imaginary part off the real axis).
-    const bool sign = ctx->use_signmap && ctx->use_window && !d_jitter && !g.large && !g.col4 && g.lh == 12 && nbins > 0 &&
+    const bool sign = ctx->use_signmap && !ctx->adaptive && ctx->use_window && !d_jitter && !g.large && !g.col4 && g.lh == 12 && nbins > 0 &&
                       win.rows > 0 && win.rows <= 2048 && !win.mirrored && alpha >= 1e-6 && alpha <= 3.14159 && signmap_supported(L);
     if (sign) {
         int rc2 = ensure(ctx, S.signmap, (size_t)nimg * 3 * sign_map_words(g.ld) * sizeof(uint32_t));
         if (rc2) return rc2;
         fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha;
     }
+    if (ctx->adaptive) fo.win = nullptr;  // the medians (S:1124) need the whole spectrum
     int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, fo);
     if (rc) return rc;
+    const double* amed = nullptr;
+    if (ctx->adaptive) {
+        MedianWork mw;
+        median_work_carve(mw, S.med.p, nimg * 3, cand_cap_for(g.P));
+        ProfScope ps(ctx, L.stream, TFFT_K_MEDIAN, (double)nimg * 3.0 * 16.0 * (double)g.E);
+        CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), 0.0, 0.0, 0.0, mw, (double*)S.medians.p, nullptr));
+        amed = (const double*)S.medians.p;
+    }
     if (sign) {
         const uint32_t* bm = (const uint32_t*)S.signmap.p;
         ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (4.0 + 4.0));
@@ -477,11 +488,11 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
     }
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
-        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
     } else {
-        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins));
+        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
         CK(launch_extract(L, spec, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
-                          d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins));
+                          d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins, amed));
     }
     return TFFT_OK;
 }
@@ -615,16 +626,14 @@ int tfft_create(int device, tfft_ctx** out) {
     ctx->total_mem = tot;
     ctx->ws_limit = (size_t)((double)tot * 0.40);
     const char* impl = getenv("TFFT_FFT_IMPL");  // "v0" forces the baseline shared-memory kernel
-    ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : (impl && !strcmp(impl, "lsu")) ? 2 : 1;  // "lsu": columns via cp.async/STG
+    ctx->fft_impl = (impl && !strcmp(impl, "v0")) ? 0 : 1;
     if (const char* hc = getenv("TFFT_HOST_CHUNK")) { int v = atoi(hc); if (v >= 1 && v <= MAX_CHUNK) HOST_CHUNK = v; }
     if (const char* hs = getenv("TFFT_HOST_SLOTS")) { int v = atoi(hs); if (v >= 1 && v <= NSLOT) HOST_SLOTS = v; }
     const char* spc = getenv("TFFT_SPECTRUM");  // "full" keeps the complete PH x PW spectrum (no Hermitian halving)
     ctx->use_half = !(spc && !strcmp(spc, "full"));
     if (const char* wd = getenv("TFFT_WIDE")) ctx->use_wide = atoi(wd) != 0;
-    if (const char* cs = getenv("TFFT_COL_SAMPLE")) ctx->col_sample = atoi(cs) != 0;
     if (const char* ew = getenv("TFFT_EXTRACT_WINDOW")) ctx->use_window = atoi(ew) != 0;
     if (const char* sm = getenv("TFFT_SIGNMAP")) ctx->use_signmap = atoi(sm) != 0;
-    if (const char* sq = getenv("TFFT_SCAN_Q32")) ctx->use_q32 = atoi(sq) != 0;
     if (const char* fe = getenv("TFFT_FUSED_EMBED")) ctx->use_fused = atoi(fe) != 0;
     for (int i = 0; i < NSLOT; i++)
         if ((e = cudaStreamCreateWithFlags(&ctx->slot[i].stream, cudaStreamNonBlocking)) != cudaSuccess) break;
@@ -680,6 +689,13 @@ const char* tfft_kind_name(int kind) {
     static const char* names[TFFT_K_COUNT] = {"row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter",
                                               "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused"};
     return (kind >= 0 && kind < TFFT_K_COUNT) ? names[kind] : "?";
+}
+
+int tfft_set_adaptive_alpha(tfft_ctx* ctx, int on) {
+    if (!ctx) return TFFT_E_INVALID;
+    ctx->adaptive = on != 0;
+    ctx->res_n = 0;  // resident spectra carry no medians
+    return TFFT_OK;
 }
 
 int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes) {
@@ -930,6 +946,11 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
     Launcher L = make_launcher(ctx, S.stream);
     if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center, &ctx->res_spec))) return rc;
+    if (ctx->adaptive) {  // S:1124: the medians of the stego spectra scale alpha in read_bit_from_bin
+        MedianWork mw;
+        median_work_carve(mw, S.med.p, n * 3, cand_cap_for(g.P));
+        CK(launch_median_capacity(L, ctx->res_spec, n * 3, g.lay(), 0.0, 0.0, 0.0, mw, (double*)S.medians.p, nullptr));
+    }
     CK(cudaStreamSynchronize(S.stream));
     ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay();
     return TFFT_OK;
@@ -953,7 +974,8 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
     ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (16.0 + 4.0));
     CK(launch_extract(L, (const double2*)ctx->res_spec, n, ctx->res_lay, (const uint32_t*)ctx->bins.p, nbins, rep,
                       jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
-                      out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr));
+                      out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr, 0,
+                      ctx->adaptive ? (const double*)S.medians.p : nullptr));
     if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes, S.outbytes.p, (size_t)n * nb, cudaMemcpyDeviceToHost, S.stream));
     if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits, S.raw.p, (size_t)n * nbins, cudaMemcpyDeviceToHost, S.stream));
     CK(cudaStreamSynchronize(S.stream));

@@ -1217,18 +1217,17 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
         const uint64_t ntiles = (E + SCAN_TILE - 1) / SCAN_TILE;
         // ~7 tiles (28 K elements, ~340 members) per CTA: the members fit the CTA's staging buffer (an overflowing CTA
         // falls back to one global atomic per member, which is what made fewer, longer CTAs slower)
-        static const unsigned cap_env = getenv("TFFT_SCAN_CTAS") ? (unsigned)atoi(getenv("TFFT_SCAN_CTAS")) : 0u;  // experiment switch
-        unsigned cc = cap_env ? cap_env : (unsigned)((ntiles + 6) / 7);
+        unsigned cc = (unsigned)((ntiles + 6) / 7);
         if (cc < 1) cc = 1;
         const unsigned per_plane = (unsigned)(ntiles < cc ? ntiles : cc);
         if (q64) {
             const uint64_t nt4 = (E / 4 + SCAN_TILE - 1) / SCAN_TILE;
-            unsigned c4 = cap_env ? cap_env : (unsigned)((nt4 + 1) / 2);
+            unsigned c4 = (unsigned)((nt4 + 1) / 2);
             if (c4 < 1) c4 = 1;
             median_scan_q64<<<dim3((unsigned)(nt4 < c4 ? nt4 : c4), (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>((const uint4*)qhi, qlo, lay, w, br, cap);
         } else if (q32 && lay.half && PH == 4096 && !all) {
             const uint64_t nt4 = (E / 4 + SCAN_TILE - 1) / SCAN_TILE;  // tiles of float4 (four elements each)
-            unsigned c4 = cap_env ? cap_env : (unsigned)((nt4 + 1) / 2);  // ~2 tiles (32 K elements) per CTA, as above
+            unsigned c4 = (unsigned)((nt4 + 1) / 2);  // ~2 tiles (32 K elements) per CTA, as above
             if (c4 < 1) c4 = 1;
             median_scan_q32<<<dim3((unsigned)(nt4 < c4 ? nt4 : c4), (unsigned)nplanes), SCAN_THREADS, 0, L.stream>>>((const float4*)q32, spec, lay, w, br, cap);
         } else {
@@ -1293,7 +1292,8 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
 __global__ void __launch_bounds__(256) embed_scatter(double2* spec, SpecLayout lay, const uint32_t* __restrict__ bins,
                                                      const uint8_t* __restrict__ bits, size_t nbits,
                                                      const double* __restrict__ jitter, double alpha,
-                                                     double cos_a, double sin_a, const uint64_t* __restrict__ usable) {
+                                                     double cos_a, double sin_a, const uint64_t* __restrict__ usable,
+                                                     const double* __restrict__ median /*adaptive alpha: [nimg*3], else null*/) {
     const int img = blockIdx.y;
     if (usable && usable[img] < (uint64_t)nbits) return;  // S:1009: over capacity -> image untouched
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1312,8 +1312,10 @@ __global__ void __launch_bounds__(256) embed_scatter(double2* spec, SpecLayout l
     const double mag = fmax(1e-12, hypot(z.x, z.y));
     const int bit = bits[(size_t)img * nbits + i];
     double c, s;
-    if (jitter) {
-        const double theta = (bit ? alpha : -alpha) + jitter[i];
+    if (jitter || median) {
+        double al = alpha;
+        if (median) al *= fmin(2.0, fmax(0.5, mag / fmax(1e-12, median[img * 3 + p])));  // compute_adaptive_alpha S:704-710
+        const double theta = (bit ? al : -al) + (jitter ? jitter[i] : 0.0);
         sincos(theta, &s, &c);
     } else {
         c = cos_a;                 // cos(-a) == cos(a), sin(-a) == -sin(a) exactly
@@ -1330,10 +1332,10 @@ __global__ void __launch_bounds__(256) embed_scatter(double2* spec, SpecLayout l
 
 cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,
                          const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
-                         double alpha, double cos_a, double sin_a, const uint64_t* usable) {
+                         double alpha, double cos_a, double sin_a, const uint64_t* usable, const double* adaptive_median) {
     if (nbits == 0 || nimg == 0) return cudaSuccess;
     dim3 grid((unsigned)((nbits + 255) / 256), (unsigned)nimg);
-    embed_scatter<<<grid, 256, 0, L.stream>>>(spec, lay, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable);
+    embed_scatter<<<grid, 256, 0, L.stream>>>(spec, lay, bins, bits, nbits, jitter, alpha, cos_a, sin_a, usable, adaptive_median);
     TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }
@@ -1442,6 +1444,12 @@ __device__ __forceinline__ int read_bit(double2 z, double alpha, double jit) {
     const double th = atan2(z.y, z.x);
     return ang_diff(th, jit + alpha) <= ang_diff(th, jit - alpha) ? 1 : 0;
 }
+// compute_adaptive_alpha (S:704-710) on the read side (S:737-738): alpha scaled by |F| / median, clamped to [0.5, 2]
+__device__ __forceinline__ double adaptive_alpha(double2 z, double alpha, const double* __restrict__ median, int img, uint32_t b) {
+    if (!median) return alpha;
+    const double mag = fmax(1e-12, hypot(z.x, z.y));
+    return alpha * fmin(2.0, fmax(0.5, mag / fmax(1e-12, median[img * 3 + (int)(b >> 30)])));
+}
 __device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, int img, const SpecLayout& lay, uint32_t b) {
     const uint32_t lin = b & 0x3FFFFFFFu;
     return spec_load(spec + (size_t)(img * 3 + (int)(b >> 30)) * lay.plane_elems(), lay, (int)(lin / (uint32_t)lay.PW), (int)(lin % (uint32_t)lay.PW));
@@ -1449,17 +1457,18 @@ __device__ __forceinline__ double2 load_bin(const double2* __restrict__ spec, in
 
 __global__ void __launch_bounds__(256) extract_raw(const double2* __restrict__ spec, SpecLayout P, const uint32_t* __restrict__ bins,
                                                    size_t nbins, const double* __restrict__ jitter, double alpha,
-                                                   uint8_t* raw_bits, size_t raw_stride) {
+                                                   uint8_t* raw_bits, size_t raw_stride, const double* __restrict__ median) {
     const int img = blockIdx.y;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbins) return;
-    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
+    const double2 z = load_bin(spec, img, P, bins[i]);
+    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)read_bit(z, adaptive_alpha(z, alpha, median, img, bins[i]), jitter ? jitter[i] : 0.0);
 }
 
 // one thread per decoded bit; a warp packs 32 decoded bits into 4 bytes with a ballot
 __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ spec, SpecLayout P, const uint32_t* __restrict__ bins,
                                                     size_t ndec, int rep, const double* __restrict__ jitter, double alpha,
-                                                    uint8_t* out_bytes, size_t nbytes) {
+                                                    uint8_t* out_bytes, size_t nbytes, const double* __restrict__ median) {
     const int img = blockIdx.y;
     const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int bit = 0;
@@ -1467,7 +1476,8 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
         int s = 0;
         for (int j = 0; j < rep; j++) {
             const size_t i = d * rep + j;
-            s += read_bit(load_bin(spec, img, P, bins[i]), alpha, jitter ? jitter[i] : 0.0);
+            const double2 z = load_bin(spec, img, P, bins[i]);
+            s += read_bit(z, adaptive_alpha(z, alpha, median, img, bins[i]), jitter ? jitter[i] : 0.0);
         }
         bit = (s >= rep / 2 + 1) ? 1 : 0;  // >=2 of 3, >=4 of 7 (rep 1: the bit itself)
     }
@@ -1551,16 +1561,16 @@ cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t n
 
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout P,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
-                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride) {
+                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride, const double* adaptive_median) {
     if (nimg == 0) return cudaSuccess;
     if (raw_bits && nbins) {
-        extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits, raw_stride ? raw_stride : nbins);
+        extract_raw<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, nbins, jitter, alpha, raw_bits, raw_stride ? raw_stride : nbins, adaptive_median);
         TFFT_LAUNCH_CHECK(L);
     }
     const size_t ndec = nbins / (size_t)rep;
     const size_t nbytes = (ndec + 7) / 8;
     if (out_bytes && nbytes) {
-        extract_vote<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, ndec, rep, jitter, alpha, out_bytes, nbytes);
+        extract_vote<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(spec, P, bins, ndec, rep, jitter, alpha, out_bytes, nbytes, adaptive_median);
         TFFT_LAUNCH_CHECK(L);
     }
     return cudaSuccess;

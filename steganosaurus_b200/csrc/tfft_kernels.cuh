@@ -144,12 +144,14 @@ bool fused_embed_supported(const Launcher& L);  // PassArgs::fused_embed is avai
 // ---- embed scatter (write_bit_on_bin S:712-732) -----------------------------------------
 cudaError_t launch_embed(const Launcher& L, double2* spec, int nimg, SpecLayout lay,
                          const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
-                         double alpha, double cos_a, double sin_a, const uint64_t* usable);
+                         double alpha, double cos_a, double sin_a, const uint64_t* usable,
+                         const double* adaptive_median = nullptr /* [nimg*3]: alpha scaled by |F| / median (S:704-710) */);
 
 // ---- extract gather + vote (read_bit_from_bin S:734-746, rep3/7 S:468/S:501, pack S:447) --
 cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, SpecLayout lay,
                            const uint32_t* bins, size_t nbins, int rep, const double* jitter, double alpha,
-                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+                           uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0,
+                           const double* adaptive_median = nullptr /* [nimg*3], S:737-738 */);
 
 // the same votes from a sign map (PassArgs::signmap) of planes with `cols` stored columns; bins must not need the mirror
 cudaError_t launch_extract_signmap(const Launcher& L, const uint32_t* signmap, int cols, int nimg, SpecLayout lay,

@@ -143,24 +143,6 @@ __device__ __forceinline__ void unit_bar(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Ping-pong between the two units of a CTA.  A unit alternates FP64-bound phases (butterflies) and LSU-bound phases
-// (exchanges, global stores); two free-running units share both pipes evenly, which keeps them in step and
-// leaves each pipe idle while the other is busy (measured: the second unit added only 15 %).  With the token
-// the LSU-bound phases strictly alternate between the units, so one unit's butterflies run under the other's
-// exchange.  acquire = bar.sync on my token (my 256 threads + 256 arrivals of the other unit), release = bar.arrive
-// on the other unit's token.  Unit 0 goes first (unit 1 pre-arrives once); `on` is switched off for the items
-// the other unit does not have, and unit 1 skips its very last release, so every barrier phase is complete.
-struct PingPong {
-    int me, other;
-    bool on;
-    __device__ __forceinline__ void acquire() const {
-        if (on) asm volatile("bar.sync %0, 512;\n" ::"r"(me) : "memory");
-    }
-    __device__ __forceinline__ void release() const {
-        if (on) asm volatile("bar.arrive %0, 512;\n" ::"r"(other) : "memory");
-    }
-};
-
 // ---- TMA (cp.async.bulk.tensor) + mbarrier primitives ------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* b, int n) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(n) : "memory");
@@ -329,7 +311,7 @@ __device__ __forceinline__ void stage23(double* X, int tt, int c, double2 w1, do
 // Variant for passes whose L buffer is not a landing buffer (u8 forward rows): exchange 2 runs in
 // place in L with 16 B entries and the same XOR swizzle -> one barrier instead of three.
 template <int S, int LOG2N, bool PADDED = false>
-__device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, double2* x, int bar_id, const PingPong pp = PingPong{0, 0, false}) {
+__device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, double2* x, int bar_id) {
     using G = Geo<LOG2N, 1>;
     const int k1 = tt >> 4, m = tt & 15;
     dft<S, 16>(x);
@@ -337,7 +319,6 @@ __device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, 
     const int k1r = tt & (G::R1 - 1), k2r = tt / G::R1;
     [[maybe_unused]] double2* Lw = L + xpos<G::R1>(k1, 0, m);   // R1 == 16: the 16 accesses are Lw[16 k2] / Lr[n] (immediate offsets)
     [[maybe_unused]] const double2* Lr = L + xpos<G::R1>(k1r, k2r, 0);
-    pp.acquire();
 #pragma unroll
     for (int k2 = 0; k2 < 16; k2++) {
         if constexpr (PADDED && G::R1 == 16) Lw[k2 << 4] = x[oidx<16>(k2)];
@@ -349,7 +330,6 @@ __device__ __forceinline__ void stage23_inplace(double2* L, int tt, double2 w1, 
         if constexpr (PADDED && G::R1 == 16) x[n] = Lr[n];
         else x[n] = L[(PADDED ? xpos<G::R1>(k1r, k2r, n) : swz<G::R1>(k1r, k2r, n))];
     }
-    pp.release();
     dft<S, 16>(x);
 }
 
@@ -1195,7 +1175,6 @@ struct R2CArgs {
     uint8_t* img_out;
     long long nitems;   // nimg * ceil(H/2) row pairs
     int W, H, PW, PH, ld, center;
-    int pingpong;       // experiment switch (TFFT_PINGPONG=1): LSU phases of the two units of a CTA strictly alternate
 };
 
 // ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
@@ -1268,19 +1247,9 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         while (clock64() - t0 < STAGGER_CYCLES) {}
     }
     unit_bar(bar_id, G::UT);
-    // ping-pong with the other unit (two-unit CTAs only): tokens are used for the items both units have
-    long long common = 0;
-    if (UNITS == 2 && a.pingpong) {
-        const long long first1 = (long long)blockIdx.x * UNITS + 1;
-        common = first1 < a.nitems ? (a.nitems - 1 - first1) / stride + 1 : 0;
-    }
-    PingPong pp{8 + unit, 8 + (unit ^ 1), common > 0};
-    if (unit == 1) pp.release();  // unit 0 goes first
-    long long jitem = 0;
     int buf = 0;
     if (item < a.nitems) issue_rows(item, 0);
-    for (; item < a.nitems; item += stride, buf ^= 1, jitem++) {
-        pp.on = jitem < common;
+    for (; item < a.nitems; item += stride, buf ^= 1) {
         cp_async_wait_all();
         unit_bar(bar_id, G::UT);
         if (item + stride < a.nitems) issue_rows(item + stride, buf ^ 1);
@@ -1313,18 +1282,15 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                 double2 w1 = a.tw[(size_t)m << (TW_LOG2 - LOG2N)];
                 twiddle<G::R1>(xj, w1);
             }
-            pp.acquire();  // LSU phase 1: exchange 1
 #pragma unroll
             for (int j = 0; j < G::J1; j++)
 #pragma unroll
                 for (int k = 0; k < G::R1; k++) L[k * 256 + tt + j * G::TP] = x[j * G::R1 + oidx<G::R1>(k)];
             unit_bar(bar_id, G::UT);
             stage2_load<LOG2N, 1>(L, tt, 0, x);
-            pp.release();
             unit_bar(bar_id, G::UT);
-            stage23_inplace<+1, LOG2N, true>(L, tt, ttw.s2v(), x, bar_id, pp);  // LSU phase 2 inside; x[oidx(k3)] = Z[tt + TP*k3]
-            if (pp.on) pp.acquire();          // LSU phase 3: split + stores (the token sync also orders the reads of L)
-            else unit_bar(bar_id, G::UT);     // all reads of L done
+            stage23_inplace<+1, LOG2N, true>(L, tt, ttw.s2v(), x, bar_id);  // x[oidx(k3)] = Z[tt + TP*k3]
+            unit_bar(bar_id, G::UT);          // all reads of L done
             // ---- split Z into the spectra of the two real rows: partners Z[N-k] through L
 #pragma unroll
             for (int k3 = 8; k3 < 16; k3++) L[tt + G::TP * (k3 - 8)] = x[oidx<16>(k3)];  // Z[N/2 + j] at L[j]
@@ -1369,11 +1335,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
                 }
             }
-            if (pp.on) {  // L is rewritten only after the next acquire, which syncs the unit
-                if (!(unit == 1 && ch == 2 && jitem == common - 1)) pp.release();  // unit 1 keeps its very last token
-            } else {
-                unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
-            }
+            unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
         }
     }
 }
@@ -1783,8 +1745,6 @@ cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
     a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
     a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
     a.nitems = (long long)(p.nplanes / 3) * (WIDE ? p.H : (p.H + 1) / 2);
-    static const int pingpong = getenv("TFFT_PINGPONG") ? atoi(getenv("TFFT_PINGPONG")) : 0;
-    a.pingpong = pingpong;
     return p.center ? run_r2c_c<LOG2N, UNITS, INV, true, WIDE>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false, WIDE>(L, a);
 }
 
@@ -1799,11 +1759,6 @@ template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, CO
 template <int LOG2N>
 cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     using C = Cfg<LOG2N>;
-    if constexpr (LOG2N == 12) {  // experiment switch: one unit per CTA (how much do two units overlap?)
-        static const bool one_unit = getenv("TFFT_ROW_UNITS") && atoi(getenv("TFFT_ROW_UNITS")) == 1;
-        if (one_unit && p.half && p.img_in) return run_r2c<LOG2N, 1, false>(L, p);
-        if (one_unit && p.half && p.img_out) return run_r2c<LOG2N, 1, true>(L, p);
-    }
     if (p.half && p.img_in) return run_r2c<LOG2N, C::U8F_UNITS, false>(L, p);
     if (p.half && p.img_out) return run_r2c<LOG2N, C::U8I_UNITS, true>(L, p);
     if (p.img_in) return run_u8<LOG2N, C::U8F_UNITS, false>(L, p);
@@ -1811,22 +1766,21 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     if (p.axis == 0)
         return p.inverse ? run_c2c<-1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p)
                          : run_c2c<+1, LOG2N, 1, pk::M_C2C_ROW, C::ROW_UNITS>(L, p);
-    if constexpr (LOG2N == 12) {  // warp-local exchange + permuting store (TFFT_COL_KERNEL=block keeps the 9-barrier kernel)
-        static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
+    if constexpr (LOG2N == 12) {  // warp-local exchange + permuting store
         if (p.fused_embed) {  // forward + phase write + inverse in one residency (the caller checked fused_embed_supported)
-            if (L.fft_impl != 1 || blockk || !p.qhi || !p.qlo || p.PW < 2 || p.in_rows != p.out_rows) return cudaErrorNotSupported;
+            if (L.fft_impl != 1 || !p.qhi || !p.qlo || p.PW < 2 || p.in_rows != p.out_rows) return cudaErrorNotSupported;
             bool ok = false;
             // (a 4096-row plane has more than 2048 image rows: 9 row blocks for UHD, else all 16)
             cudaError_t e = p.in_rows <= 9 * 256 ? run_col_embed_w<9, 9>(L, p, &ok) : run_col_embed_w<16, 16>(L, p, &ok);
             return (e == cudaSuccess && !ok) ? cudaErrorNotSupported : e;
         }
         if (p.signmap) {  // extract without jitter: the pass only leaves the read bits behind (the caller checked signmap_supported)
-            if (L.fft_impl != 1 || blockk || p.inverse || p.out_rows > 8 * 256 || p.PW < 2) return cudaErrorNotSupported;
+            if (L.fft_impl != 1 || p.inverse || p.out_rows > 8 * 256 || p.PW < 2) return cudaErrorNotSupported;
             bool ok = false;
             cudaError_t e = p.in_rows <= 9 * 256 ? run_col_tma_w<+1, 9, 8, true>(L, p, &ok) : run_col_tma_w<+1, 16, 8, true>(L, p, &ok);
             return (e == cudaSuccess && !ok) ? cudaErrorNotSupported : e;
         }
-        if (L.fft_impl != 2 && !blockk && p.PW >= 2) {
+        if (p.PW >= 2) {
             bool ok = false;
             // zero structure of a padded image (UHD: 2160 of 4096 rows): 9 of 16 row blocks carry data
             // forward pass of an extract: only the rows that hold bins are kept (the default annulus ends at row 0.45 * 4096)
@@ -1837,7 +1791,7 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
             if (e != cudaSuccess || ok) return e;
         }
     }
-    if (L.fft_impl != 2 && p.PW >= C::TMA_VEC) {  // TFFT_FFT_IMPL=lsu keeps the cp.async/STG column kernel
+    if (p.PW >= C::TMA_VEC) {  // (the cp.async / STG column kernel below only runs where no tensor map can be had)
         bool ok = false;
         cudaError_t e = p.inverse ? run_col_tma<-1, LOG2N, C::TMA_VEC>(L, p, &ok) : run_col_tma<+1, LOG2N, C::TMA_VEC>(L, p, &ok);
         if (e != cudaSuccess || ok) return e;
@@ -1848,10 +1802,7 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
 
 }  // namespace
 
-bool signmap_supported(const Launcher& L) {
-    static const bool blockk = getenv("TFFT_COL_KERNEL") && !strcmp(getenv("TFFT_COL_KERNEL"), "block");
-    return L.fft_impl == 1 && !blockk && get_encoder() != nullptr;
-}
+bool signmap_supported(const Launcher& L) { return L.fft_impl == 1 && get_encoder() != nullptr; }
 
 bool fused_embed_supported(const Launcher& L) { return signmap_supported(L); }
 

@@ -457,3 +457,37 @@ def test_wide_half_path_matches_unfused_path():
     assert np.allclose(a[2], b[2], rtol=1e-11)
     assert np.array_equal(a[3], b[3])
     assert (a[3][0] != bits[0]).mean() < 0.5
+
+
+@pytest.mark.parametrize("W,H", [(512, 512), (600, 2160), (300, 200)])
+def test_adaptive_alpha_hook(W, H):
+    """Params.adaptive_alpha (S:379, S:704-710; experimental upstream): alpha scaled by |F| / median per bin in
+    write_bit_on_bin and read_bit_from_bin.  The reference's own functions with adaptive_alpha = true are the oracle."""
+    if not O.have_ref():
+        pytest.skip("oracle/_ref not shipped")
+    r = O.ref()
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    nbits = 6000
+    cover = synth.gen_texture(W, H, 7 * W + H)
+    bins = synth.random_bins(PH, PW, nbits, 3)
+    bits = synth.random_bits(1, nbits, 4)
+    plain = r.embed(cover, bins, bits[0])["stego"]
+    r.set_adaptive(True)
+    try:
+        want = r.embed(cover, bins, bits[0])
+        _, wraw = r.extract(want["stego"], bins, 1)
+    finally:
+        r.set_adaptive(False)
+    assert not np.array_equal(plain, want["stego"])  # the switch does something
+    with sb.Context(0) as c:
+        c.set_adaptive_alpha(True)
+        stego, usable, med = c.embed_batch(cover[None], bins, bits)
+        _, raw = c.extract_bits(want["stego"][None], bins, 1)
+        c.forward_batch(want["stego"][None])
+        _, raw2 = c.read_bits(bins, 1)
+        c.set_adaptive_alpha(False)
+        s0, _, _ = c.embed_batch(cover[None], bins, bits)
+    assert_pixels(stego[0], want["stego"])
+    assert int(usable[0]) == want["usable"]
+    assert np.array_equal(raw[0], wraw) and np.array_equal(raw2[0], wraw)
+    assert_pixels(s0[0], plain)
