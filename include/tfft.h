@@ -169,6 +169,40 @@ int tfft_median_capacity_dev(tfft_ctx* ctx, const double* d_spec_c64, int n, int
  * plane index above 2 or a bin outside the PH x PW plane. */
 int tfft_bin_window(const uint32_t* bins, size_t nbins, int W, int H, int half, int* rows, int* cols, int* mirrored);
 
+/* ---- config 5: ONE image too large to be worth replicating, its 2-D FFT slab-decomposed over G GPUs ------------------
+ * (fft2d S:359-366 distributed).  One process / context per GPU.  Rank g owns image rows
+ * [g R, (g+1) R), R = PH / G; after the exchange it owns the COLUMN slab [3][PH][cols] of the half spectrum (real
+ * planes are Hermitian: columns 0..PW/2, padded to ld = PW/2 + 16; cols = ld / G, columns [g cols, (g+1) cols)).
+ * The library does the passes and the data movement; the caller provides the transport: either peer-mapped
+ * destination pointers (tfft_ipc_*; the split kernel then stores straight into the other GPUs' slabs over NVLink) or
+ * a local send buffer that it hands to a collective.  All pointers are device pointers, all calls enqueue on `stream`.
+ * G in {1,2,4,8}; PW, PH in [512, 16384]; PH / G >= 2; no capacity gate on this path (a frame that fits an image this
+ * size is orders of magnitude below its capacity; S:1009 is checked by the caller if at all). */
+int tfft_slab_sizes(int W, int H, int G, int* PW, int* PH, int* R, int* ld, int* cols);
+/* forward, step 1: my image rows [nrows][W][3] (image rows y0 = g R ...; nrows = rows of the image inside my slab,
+ * possibly 0) -> pair rows -> row FFT -> Hermitian split; element (plane, image row y, column k) is stored at
+ * dst[k / cols] + plane * plane_stride + (y - row_base) * cols + k % cols  (units: complex doubles).
+ *   peer slabs:   dst[d] = rank d's column slab, plane_stride = PH * cols, row_base = 0
+ *   send buffer:  dst[d] = send + d * R * cols,  plane_stride = G * R * cols, row_base = g * R   (per plane [G][R][cols]) */
+int tfft_slab_rows_forward_dev(tfft_ctx* ctx, const uint8_t* d_rows, int nrows, int W, int H, int G, int g, int center,
+                               double* const* dst, size_t plane_stride, int row_base, void* stream);
+/* column pass over PH points on my column slab [3][PH][cols], in place (inverse: e^{-i}, scaled by 1/PH) */
+int tfft_slab_cols_dev(tfft_ctx* ctx, double* d_colslab, int W, int H, int G, int inverse, void* stream);
+/* phase write (S:712-732) / phase read (S:734-746; d_raw[i] = 0/1, or -1 when bin i lives on another rank) on my slab */
+int tfft_slab_embed_dev(tfft_ctx* ctx, double* d_colslab, int W, int H, int G, int g, const uint32_t* d_bins,
+                        const uint8_t* d_bits, size_t nbits, double alpha, void* stream);
+int tfft_slab_read_dev(tfft_ctx* ctx, const double* d_colslab, int W, int H, int G, int g, const uint32_t* d_bins,
+                       size_t nbins, double alpha, int8_t* d_raw, void* stream);
+/* inverse, last step: tiles [3][G][R][cols] (tile s = my rows of rank s's column slab after its inverse column pass)
+ * -> pair rows -> inverse row FFT -> crop / centre / round / clamp -> my rows of the stego image [nrows][W][3] */
+int tfft_slab_rows_inverse_dev(tfft_ctx* ctx, const double* d_tiles, int nrows, int W, int H, int G, int g, int center,
+                               uint8_t* d_rows_out, void* stream);
+/* CUDA IPC for the peer transport: export a cudaMalloc'd buffer / map another process's buffer (peer access is enabled
+ * on demand) / unmap it.  handle = 64 bytes (cudaIpcMemHandle_t). */
+int tfft_ipc_export(const void* d_ptr, unsigned char handle[64]);
+int tfft_ipc_open(int device, const unsigned char handle[64], void** d_ptr);
+int tfft_ipc_close(void* d_ptr);
+
 /* ---- per-kernel timing (CUDA events on the launching stream) -------------------------------
  * When enabled, every kernel group the library launches is bracketed by a pair of events; after
  * the caller has synchronised, tfft_profile_read() returns launches and summed device time per
@@ -184,7 +218,8 @@ enum {
     TFFT_K_C2C = 7,      /* plain c64 pass from the fft2d / fft_pass hooks */
     TFFT_K_COL_FWD_WIN = 8, /* column FFT of an extract: only the columns / rows that hold bins */
     TFFT_K_COL_EMBED = 9,   /* column-resident embed: forward columns + phase write + inverse columns in one pass */
-    TFFT_K_COUNT = 10
+    TFFT_K_SLAB = 10,       /* config 5 glue: pair pack, split + scatter (the exchange), tile merge, u8 quantise */
+    TFFT_K_COUNT = 11
 };
 int tfft_profile_enable(tfft_ctx* ctx, int on);
 int tfft_profile_reset(tfft_ctx* ctx);

@@ -19,6 +19,8 @@ SYMBOLS = [
     "tfft_forward_batch", "tfft_read_bits", "tfft_forward_spectrum", "tfft_fft2d", "tfft_fft2d_dev",
     "tfft_fft_pass_dev", "tfft_median_capacity_dev", "tfft_extract_frame", "tfft_extract_frame_dev",
     "tfft_profile_enable", "tfft_profile_reset", "tfft_profile_read", "tfft_kind_name", "tfft_bin_window",
+    "tfft_slab_sizes", "tfft_slab_rows_forward_dev", "tfft_slab_cols_dev", "tfft_slab_embed_dev", "tfft_slab_read_dev",
+    "tfft_slab_rows_inverse_dev", "tfft_ipc_export", "tfft_ipc_open", "tfft_ipc_close",
 ]
 
 _lib = None
@@ -96,5 +98,24 @@ def load() -> C.CDLL:
     L.tfft_median_capacity_dev.restype = i
     L.tfft_bin_window.argtypes = [vp, sz, i, i, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.tfft_bin_window.restype = i
+    ip = C.POINTER(i)
+    L.tfft_slab_sizes.argtypes = [i, i, i, ip, ip, ip, ip, ip]
+    L.tfft_slab_sizes.restype = i
+    L.tfft_slab_rows_forward_dev.argtypes = [vp, vp, i, i, i, i, i, i, C.POINTER(vp), sz, i, vp]
+    L.tfft_slab_rows_forward_dev.restype = i
+    L.tfft_slab_cols_dev.argtypes = [vp, vp, i, i, i, i, vp]
+    L.tfft_slab_cols_dev.restype = i
+    L.tfft_slab_embed_dev.argtypes = [vp, vp, i, i, i, i, vp, vp, sz, d, vp]
+    L.tfft_slab_embed_dev.restype = i
+    L.tfft_slab_read_dev.argtypes = [vp, vp, i, i, i, i, vp, sz, d, vp, vp]
+    L.tfft_slab_read_dev.restype = i
+    L.tfft_slab_rows_inverse_dev.argtypes = [vp, vp, i, i, i, i, i, i, vp, vp]
+    L.tfft_slab_rows_inverse_dev.restype = i
+    L.tfft_ipc_export.argtypes = [vp, C.c_char_p]
+    L.tfft_ipc_export.restype = i
+    L.tfft_ipc_open.argtypes = [i, C.c_char_p, C.POINTER(vp)]
+    L.tfft_ipc_open.restype = i
+    L.tfft_ipc_close.argtypes = [vp]
+    L.tfft_ipc_close.restype = i
     _lib = L
     return L

@@ -214,7 +214,7 @@ class Context:
                                                   _dptr(raw_bits), self._stream()))
 
     # ------------------------------------------------------------------ per-kernel timing
-    KINDS = ["row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter", "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused"]
+    KINDS = ["row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter", "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused", "slab_glue"]
 
     def profile_enable(self, on=True):
         self._check(self.L.tfft_profile_enable(self.h, int(on)))

@@ -64,6 +64,7 @@ struct tfft_ctx {
     unsigned* d_win = nullptr;  // device-pointer entry points: bin window reduced on the device ...
     unsigned* h_win = nullptr;  // ... and read back through this pinned pair
     DevBuf full;            // expansion target of the tfft_forward_spectrum hook
+    DevBuf slab_z, slab_tmp;  // config 5: pair rows [3][R/2][PW] and the scratch batch of their four-step row passes
     SpecLayout res_lay{0, 0, 0, 0};
     // resident spectra for the two-phase extract
     int res_n = 0, res_PH = 0, res_PW = 0;
@@ -657,7 +658,7 @@ void tfft_destroy(tfft_ctx* ctx) {
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
     }
-    release(ctx->bins); release(ctx->jitter); release(ctx->full); release(ctx->pres);
+    release(ctx->bins); release(ctx->jitter); release(ctx->full); release(ctx->pres); release(ctx->slab_z); release(ctx->slab_tmp);
     prof_drain(ctx);
     for (cudaEvent_t ev : ctx->prof_pool) cudaEventDestroy(ev);
     if (ctx->d_tw) cudaFree(ctx->d_tw);
@@ -687,7 +688,7 @@ int tfft_profile_read(tfft_ctx* ctx, int kind, uint64_t* groups, double* total_m
 }
 const char* tfft_kind_name(int kind) {
     static const char* names[TFFT_K_COUNT] = {"row_fwd_u8", "col_fwd", "median_capacity", "embed_scatter",
-                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused"};
+                                              "col_inv", "row_inv_u8", "extract_vote", "c2c_pass", "col_fwd_window", "col_embed_fused", "slab_glue"};
     return (kind >= 0 && kind < TFFT_K_COUNT) ? names[kind] : "?";
 }
 
@@ -1077,6 +1078,172 @@ int tfft_fft2d(tfft_ctx* ctx, double* data, int n, int PH, int PW, int inverse) 
         CK(cudaMemcpyAsync(data + i0 * P * 2, S.spec.p, m * pb, cudaMemcpyDeviceToHost, S.stream));
         CK(cudaStreamSynchronize(S.stream));
     }
+    return TFFT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// config 5: slab-decomposed 2-D FFT (kernels in tfft_slab.cu)
+namespace {
+struct SlabGeom { int W, H, G, PW, PH, R, ld, cols, lw, lh, npairs; };
+int slab_geom(int W, int H, int G, SlabGeom& s) {
+    if (W <= 0 || H <= 0 || !(G == 1 || G == 2 || G == 4 || G == 8)) return TFFT_E_INVALID;
+    s.W = W; s.H = H; s.G = G;
+    s.PW = next_pow2_i(W); s.PH = next_pow2_i(H);
+    if (s.PW > TFFT_MAX_DIM || s.PH > TFFT_MAX_DIM || s.PW < 512 || s.PH < 512) return TFFT_E_UNSUPPORTED;
+    s.lw = ilog2(s.PW); s.lh = ilog2(s.PH);
+    s.R = s.PH / G;
+    s.ld = s.PW / 2 + 16;
+    if (s.R < 2 || s.ld % G) return TFFT_E_UNSUPPORTED;
+    s.cols = s.ld / G;
+    s.npairs = s.R / 2;
+    return TFFT_OK;
+}
+// one c2c pass over the pair rows [3][npairs][PW] along x; returns the buffer that holds the result (four-step passes
+// leave it in the scratch batch instead of copying it back)
+int slab_row_pass(tfft_ctx* ctx, const Launcher& L, const SlabGeom& s, int inverse, double2** where) {
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.spec = (double2*)ctx->slab_z.p; a.tmp = (double2*)ctx->slab_tmp.p; a.tw = ctx->d_tw;
+    a.nplanes = 3; a.W = s.PW; a.H = s.npairs; a.PW = s.PW; a.PH = s.npairs;
+    a.in_rows = s.npairs; a.out_rows = s.npairs; a.inverse = inverse; a.ld = s.PW;
+    a.axis = 0; a.log2n = s.lw;
+    const bool four = s.lw > 12;
+    a.leave_in_tmp = four ? 1 : 0;
+    ProfScope ps(ctx, L.stream, TFFT_K_C2C, 3.0 * 32.0 * (double)s.npairs * s.PW * (four ? 2.0 : 1.0));
+    CK(launch_fft_pass(L, a));
+    *where = four ? a.tmp : a.spec;
+    return TFFT_OK;
+}
+int slab_ensure_rows(tfft_ctx* ctx, const SlabGeom& s) {
+    int rc;
+    const size_t b = (size_t)3 * s.npairs * s.PW * sizeof(double2);
+    if ((rc = ensure(ctx, ctx->slab_z, b))) return rc;
+    if (s.lw > 12 && (rc = ensure(ctx, ctx->slab_tmp, b))) return rc;
+    return TFFT_OK;
+}
+}  // namespace
+
+int tfft_slab_sizes(int W, int H, int G, int* PW, int* PH, int* R, int* ld, int* cols) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (PW) *PW = s.PW;
+    if (PH) *PH = s.PH;
+    if (R) *R = s.R;
+    if (ld) *ld = s.ld;
+    if (cols) *cols = s.cols;
+    return TFFT_OK;
+}
+
+int tfft_slab_rows_forward_dev(tfft_ctx* ctx, const uint8_t* d_rows, int nrows, int W, int H, int G, int g, int center,
+                               double* const* dst, size_t plane_stride, int row_base, void* stream) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (!ctx || !dst || g < 0 || g >= G || nrows < 0 || nrows > s.R || (nrows && !d_rows)) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = slab_ensure_rows(ctx, s))) return rc;
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    double2* z = (double2*)ctx->slab_z.p;
+    const double pz = 3.0 * 16.0 * (double)s.npairs * s.PW;
+    { ProfScope ps(ctx, L.stream, TFFT_K_SLAB, (double)nrows * W * 3 + pz); CK(launch_slab_pack(L, d_rows, nrows, W, s.PW, s.npairs, g * s.R, center, z)); }
+    double2* Z = nullptr;
+    if ((rc = slab_row_pass(ctx, L, s, 0, &Z))) return rc;
+    SlabDst d;
+    for (int i = 0; i < SLAB_MAX_RANKS; i++) d.p[i] = i < G ? (double2*)dst[i] : nullptr;
+    { ProfScope ps(ctx, L.stream, TFFT_K_SLAB, pz + 3.0 * 16.0 * (double)s.R * s.ld);
+      CK(launch_slab_split(L, Z, s.PW, s.ld, s.cols, s.npairs, g * s.R, d, plane_stride, row_base)); }
+    return TFFT_OK;
+}
+
+int tfft_slab_cols_dev(tfft_ctx* ctx, double* d_colslab, int W, int H, int G, int inverse, void* stream) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (!ctx || !d_colslab) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    PassArgs a;
+    memset(&a, 0, sizeof(a));
+    if (ctx->fft_impl != 0 && s.PH > 4096) {  // four-step columns: scratch batch of the slab's size
+        if ((rc = ensure(ctx, ctx->full, (size_t)3 * s.PH * s.cols * sizeof(double2)))) return rc;
+        a.tmp = (double2*)ctx->full.p;
+    }
+    a.spec = (double2*)d_colslab; a.tw = ctx->d_tw; a.nplanes = 3;
+    a.W = s.cols; a.H = s.PH; a.PW = s.cols; a.PH = s.PH;  // (the slab is a plane of `cols` columns: any even count)
+    a.in_rows = s.PH; a.out_rows = s.PH; a.inverse = inverse; a.ld = s.cols;
+    a.axis = 1; a.log2n = s.lh;
+    ProfScope ps(ctx, L.stream, TFFT_K_C2C, 3.0 * 32.0 * (double)s.PH * s.cols * (s.PH > 4096 ? 2.0 : 1.0));
+    CK(launch_fft_pass(L, a));
+    return TFFT_OK;
+}
+
+int tfft_slab_embed_dev(tfft_ctx* ctx, double* d_colslab, int W, int H, int G, int g, const uint32_t* d_bins,
+                        const uint8_t* d_bits, size_t nbits, double alpha, void* stream) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (!ctx || !d_colslab || g < 0 || g >= G || (nbits && (!d_bins || !d_bits))) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    ProfScope ps(ctx, L.stream, TFFT_K_EMBED, (double)nbits * (16.0 + 16.0 + 5.0) / G);
+    CK(launch_slab_embed(L, (double2*)d_colslab, s.PH, s.PW, s.cols, g * s.cols, d_bins, d_bits, nbits, cos(alpha), sin(alpha)));
+    return TFFT_OK;
+}
+
+int tfft_slab_read_dev(tfft_ctx* ctx, const double* d_colslab, int W, int H, int G, int g, const uint32_t* d_bins,
+                       size_t nbins, double alpha, int8_t* d_raw, void* stream) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (!ctx || !d_colslab || g < 0 || g >= G || (nbins && (!d_bins || !d_raw))) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nbins * (16.0 / G + 5.0));
+    CK(launch_slab_read(L, (const double2*)d_colslab, s.PH, s.PW, s.cols, g * s.cols, d_bins, nbins, alpha, d_raw));
+    return TFFT_OK;
+}
+
+int tfft_slab_rows_inverse_dev(tfft_ctx* ctx, const double* d_tiles, int nrows, int W, int H, int G, int g, int center,
+                               uint8_t* d_rows_out, void* stream) {
+    SlabGeom s;
+    int rc = slab_geom(W, H, G, s);
+    if (rc) return rc;
+    if (!ctx || !d_tiles || g < 0 || g >= G || nrows < 0 || nrows > s.R || (nrows && !d_rows_out)) return TFFT_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = slab_ensure_rows(ctx, s))) return rc;
+    Launcher L = make_launcher(ctx, (cudaStream_t)stream);
+    const double pz = 3.0 * 16.0 * (double)s.npairs * s.PW;
+    { ProfScope ps(ctx, L.stream, TFFT_K_SLAB, pz + 3.0 * 16.0 * (double)s.R * s.ld);
+      CK(launch_slab_merge(L, (const double2*)d_tiles, s.PW, s.cols, G, s.R, s.npairs, (double2*)ctx->slab_z.p)); }
+    double2* Z = nullptr;
+    if ((rc = slab_row_pass(ctx, L, s, 1, &Z))) return rc;
+    { ProfScope ps(ctx, L.stream, TFFT_K_SLAB, pz + (double)nrows * W * 3); CK(launch_slab_to_u8(L, Z, nrows, W, s.PW, s.npairs, g * s.R, center, d_rows_out)); }
+    return TFFT_OK;
+}
+
+int tfft_ipc_export(const void* d_ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!d_ptr || !handle) return TFFT_E_INVALID;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, (void*)d_ptr) != cudaSuccess) { cudaGetLastError(); return TFFT_E_CUDA; }
+    memcpy(handle, &h, 64);
+    return TFFT_OK;
+}
+int tfft_ipc_open(int device, const unsigned char handle[64], void** d_ptr) {
+    if (!handle || !d_ptr) return TFFT_E_INVALID;
+    *d_ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return TFFT_E_CUDA;
+    }
+    return TFFT_OK;
+}
+int tfft_ipc_close(void* d_ptr) {
+    if (!d_ptr) return TFFT_E_INVALID;
+    if (cudaIpcCloseMemHandle(d_ptr) != cudaSuccess) { cudaGetLastError(); return TFFT_E_CUDA; }
     return TFFT_OK;
 }
 

@@ -255,7 +255,11 @@ cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a) {
         if (a.log2n > 12 && a.log2n <= 14 && a.tmp && !a.img_in && !a.img_out && !a.half) return launch_fourstep(L, a);
         bool handled = false;
         cudaError_t e = launch_fft_pass_pencil(L, a, &handled);
-        if (e != cudaSuccess || handled) return e;
+        if (e == cudaErrorNotSupported && !a.img_in && !a.img_out && !a.signmap && !a.fused_embed && !a.half) {
+            cudaGetLastError();  // a plain c2c pass whose column count no pencil kernel tiles: the generic kernel takes it
+        } else if (e != cudaSuccess || handled) {
+            return e;
+        }
     }
     return launch_v0(L, a);
 }

@@ -165,6 +165,19 @@ cudaError_t launch_bins_window(const Launcher& L, const uint32_t* bins, size_t n
 cudaError_t launch_u8_to_planes(const Launcher& L, const uint8_t* img, double2* spec, int nimg, int W, int H, int PW, int PH, int center);
 cudaError_t launch_planes_to_u8(const Launcher& L, const double2* spec, uint8_t* img, int nimg, int W, int H, int PW, int PH, int center);
 
+// ---- config 5: slab-decomposed 2-D FFT over G GPUs (tfft_slab.cu) ----------------------------------------------------
+constexpr int SLAB_MAX_RANKS = 8;
+struct SlabDst { double2* p[SLAB_MAX_RANKS]; };  // per destination rank: where its columns of my half rows go (local or peer-mapped)
+cudaError_t launch_slab_pack(const Launcher& L, const uint8_t* rows, int nrows, int W, int PW, int npairs, int y0, int center, double2* z);
+cudaError_t launch_slab_split(const Launcher& L, const double2* Z, int PW, int ld, int cols, int npairs, int y0, const SlabDst& dst,
+                              size_t plane_stride, int row_base);
+cudaError_t launch_slab_merge(const Launcher& L, const double2* tiles, int PW, int cols, int G, int R, int npairs, double2* Z);
+cudaError_t launch_slab_to_u8(const Launcher& L, const double2* z, int nrows, int W, int PW, int npairs, int y0, int center, uint8_t* rows);
+cudaError_t launch_slab_embed(const Launcher& L, double2* slab, int PH, int PW, int cols, int col0, const uint32_t* bins, const uint8_t* bits,
+                              size_t nbits, double cos_a, double sin_a);
+cudaError_t launch_slab_read(const Launcher& L, const double2* slab, int PH, int PW, int cols, int col0, const uint32_t* bins, size_t nbins,
+                             double alpha, int8_t* raw);
+
 // full[y][x] from the half layout (parity hook tfft_forward_spectrum)
 cudaError_t launch_expand_half(const Launcher& L, const double2* half_spec, double2* full_spec, int nplanes, SpecLayout lay);
 

@@ -1780,7 +1780,7 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
             cudaError_t e = p.in_rows <= 9 * 256 ? run_col_tma_w<+1, 9, 8, true>(L, p, &ok) : run_col_tma_w<+1, 16, 8, true>(L, p, &ok);
             return (e == cudaSuccess && !ok) ? cudaErrorNotSupported : e;
         }
-        if (p.PW >= 2) {
+        if (p.PW >= 2 && p.PW % 2 == 0) {
             bool ok = false;
             // zero structure of a padded image (UHD: 2160 of 4096 rows): 9 of 16 row blocks carry data
             // forward pass of an extract: only the rows that hold bins are kept (the default annulus ends at row 0.45 * 4096)
@@ -1791,11 +1791,12 @@ cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
             if (e != cudaSuccess || ok) return e;
         }
     }
-    if (p.PW >= C::TMA_VEC) {  // (the cp.async / STG column kernel below only runs where no tensor map can be had)
+    if (p.PW >= C::TMA_VEC && p.PW % C::TMA_VEC == 0) {  // (the cp.async / STG column kernel below only runs where no tensor map can be had)
         bool ok = false;
         cudaError_t e = p.inverse ? run_col_tma<-1, LOG2N, C::TMA_VEC>(L, p, &ok) : run_col_tma<+1, LOG2N, C::TMA_VEC>(L, p, &ok);
         if (e != cudaSuccess || ok) return e;
     }
+    if (p.PW % C::COL_VEC) return cudaErrorNotSupported;  // (the caller falls back to the generic kernel)
     return p.inverse ? run_c2c<-1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p)
                      : run_c2c<+1, LOG2N, C::COL_VEC, pk::M_C2C_COL, C::COL_UNITS>(L, p);
 }

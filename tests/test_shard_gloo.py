@@ -81,39 +81,63 @@ def test_two_rank_gloo_timing_and_sharding():
 
 # ---------------------------------------------------------------- slab-decomposed 2-D FFT (config 5) on gloo
 def _slab_worker(rank, world, port, q):
+    """The product's SlabPlan + CollectiveTransport (zero-copy all_to_all per plane) around a numpy restatement of the
+    layout kernels (tests/slab_ref.py): forward half spectrum, embed on the owner's slab, inverse, against the dense
+    single-process computation."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from steganosaurus_b200 import slab
-        PH, PW, n = 16, 32, 3
-        g = torch.Generator().manual_seed(5)
-        full = torch.randn(n, PH, PW, dtype=torch.float64, generator=g).to(torch.complex128)  # real planes
-        sf = slab.SlabFFT2D(dist, PH, PW, slab.torch_pass_fn())
-        mine = full[:, rank * sf.rows:(rank + 1) * sf.rows, :].contiguous().clone()
-        ycols = sf.forward(mine)
-        want = torch.fft.ifft2(full) * (PH * PW)  # reference forward convention (S:347)
-        assert torch.allclose(ycols, want[:, :, rank * sf.cols:(rank + 1) * sf.cols], atol=1e-9)
-        # embed two bins (one whose mirror lives on the other rank), inverse, check against the dense computation
-        bins = torch.tensor([(0 << 30) | (2 * PW + 3), (1 << 30) | (1 * PW + 5), (2 << 30) | (3 * PW + 2)], dtype=torch.int64)
-        bits = torch.tensor([1, 0, 1])
-        dense = want.clone()
         import math
-        for b, bit in zip(bins.tolist(), bits.tolist()):
-            p, y, x = b >> 30, (b & 0x3FFFFFFF) // PW, (b & 0x3FFFFFFF) % PW
-            mag = max(1e-12, abs(dense[p, y, x].item()))
+        import numpy as np
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import slab_ref
+        from steganosaurus_b200 import slab
+        W, H = 600, 500  # pads to 1024 x 512
+        plan = slab.SlabPlan(W, H, world, rank)
+        rng = np.random.default_rng(5)
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        tr = slab.CollectiveTransport(dist)
+        send = torch.zeros(3, plan.G, plan.R, plan.cols, dtype=torch.complex128)
+        colslab = torch.zeros(3, plan.PH, plan.cols, dtype=torch.complex128)
+        tiles = torch.zeros(3, plan.G, plan.R, plan.cols, dtype=torch.complex128)
+        # the targets the CUDA split kernel is given must describe exactly this send layout
+        ptrs, pstride, row_base = tr.forward_targets(plan, 1 << 20, 0)
+        assert ptrs == [(1 << 20) + d * plan.R * plan.cols * 16 for d in range(plan.G)]
+        assert pstride == plan.G * plan.R * plan.cols and row_base == plan.y0
+        Z = slab_ref.row_pass(slab_ref.pack_pairs(img[plan.y0:plan.y0 + plan.nrows], plan, center=True))
+        send.copy_(torch.from_numpy(slab_ref.split_scatter(Z, plan)))
+        tr.forward_exchange(plan, send, colslab)
+        col = colslab.numpy()
+        col[...] = np.fft.ifft(col, axis=1) * plan.PH   # column pass
+        # dense reference
+        pad = np.zeros((3, plan.PH, plan.PW))
+        yy, xx = np.mgrid[0:H, 0:W]
+        sgn = np.where((xx + yy) & 1, -1.0, 1.0)
+        for p in range(3):
+            pad[p, :H, :W] = img[:, :, p] * sgn
+        F = np.fft.ifft2(pad) * (plan.PH * plan.PW)
+        assert np.allclose(col[:, :, :min(plan.cols, plan.PW // 2 + 1 - plan.col0)],
+                           F[:, :, plan.col0:plan.col0 + plan.cols][:, :, :min(plan.cols, plan.PW // 2 + 1 - plan.col0)], atol=1e-6)
+        # embed one bin per rank's column range on the owner, inverse, compare with the dense embed
+        bins = [(0, 3, 5), (1, 7, plan.cols + 3), (2, plan.PH - 2, 9)]
+        dense = F.copy()
+        for (p, y, x), bit in zip(bins, (1, 0, 1)):
+            mag = abs(dense[p, y, x])
             nv = complex(mag * math.cos(0.5), mag * math.sin(0.5) * (1 if bit else -1))
             dense[p, y, x] = nv
-            dense[p, (PH - y) % PH, (PW - x) % PW] = nv.conjugate()
-        sf.embed_on_cols(ycols, bins, bits, 0.5)
-        assert torch.allclose(ycols, dense[:, :, rank * sf.cols:(rank + 1) * sf.cols], atol=1e-9)
-        raw = sf.read_on_cols(ycols, bins)
-        assert raw.tolist() == bits.tolist()
-        back = sf.inverse(ycols)
-        want_back = torch.fft.fft2(dense) / (PH * PW)
-        assert torch.allclose(back, want_back[:, rank * sf.rows:(rank + 1) * sf.rows, :], atol=1e-9)
-        assert back.imag.abs().max() < 1e-9  # Hermitian by construction: the image stays real
+            dense[p, (plan.PH - y) % plan.PH, (plan.PW - x) % plan.PW] = nv.conjugate()
+            if plan.col0 <= x < plan.col0 + plan.cols:
+                col[p, y, x - plan.col0] = nv
+        col[...] = np.fft.fft(col, axis=1) / plan.PH     # inverse column pass
+        tr.inverse_exchange(plan, colslab, tiles)
+        rows = slab_ref.pairs_to_rows(slab_ref.row_pass(slab_ref.merge_tiles(tiles.numpy(), plan), inverse=True), plan)
+        want = (np.fft.fft2(dense) / (plan.PH * plan.PW)).real
+        got = rows.transpose(2, 0, 1)
+        assert np.allclose(got, want[:, plan.y0:plan.y0 + plan.R], atol=1e-6)
+        assert plan.exchange_bytes_per_plane() == (world - 1) * plan.R * plan.cols * 16
         q.put((rank, "ok"))
-    except Exception as e:  # pragma: no cover
+    except Exception:  # pragma: no cover
         import traceback
         q.put((rank, traceback.format_exc()))
     finally:
