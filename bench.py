@@ -212,6 +212,9 @@ def run_reference_arm(args):
         return 0
     if args.config == "c4":
         return run_c4_reference(args)
+    if args.config == "c5":
+        print(json.dumps({"impl": "reference", "metric": C5_METRIC, "unavailable": "one 16384^2 embed+extract is ~8 min and 35 GB on one host core (SURVEY 8d)"}), flush=True)
+        return 0
     arm = CpuArm(args.width, args.height, args.payload)
     t = cpu_measure(arm, args.warmup, args.steps)
     arm.close()
@@ -371,9 +374,136 @@ def run_c4_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# BASELINE config 5: ONE 16384 x 16384 RGB image, slab-decomposed 2-D FFT over the ranks (steganosaurus_b200/slab.py).
+# A step = embed (my rows of the cover -> my rows of the stego image) + extract (stego rows -> raw read bits of the
+# whole frame, combined over ranks).  Strong scaling: the image is fixed, the ranks share it.
+C5_METRIC = "embed+extract megapixels/sec (single 16K x 16K RGB image, slab-decomposed 2-D FFT)"
+
+
+def c5_rows(W, y0, nrows, seed):
+    """gen_png-style rows (tools/gen_png.cpp:8-17) of a tall image, generated per rank (the full 16K image costs 6 GB of host temporaries)."""
+    rng = np.random.default_rng([seed, y0])
+    x = np.arange(W, dtype=np.int32)[None, :]
+    y = (np.arange(nrows, dtype=np.int32) + y0)[:, None]
+    n = rng.integers(-10, 10, size=(nrows, W), dtype=np.int32)
+    img = np.empty((nrows, W, 3), np.int32)
+    img[:, :, 0] = 180 + (x * 40) // W + n
+    img[:, :, 1] = 180 + (y * 40) // 16384 + n
+    img[:, :, 2] = 200 + n
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def run_c5(args):
+    import torch
+    import steganosaurus_b200 as sb
+    from steganosaurus_b200 import host, slab, synth, shard
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    timing = shard.Timing(dist, dev)
+    N = args.size
+    nbits = synth.frame_len(args.payload)
+    bins_np = host.walk(b"correct horse battery staple", N, N, nbits, PARAMS["rmin"], PARAMS["rmax"], 0.7)[0]
+    bits_np = make_frame_bits(1, args.payload, 2005)[0]
+    ctx = sb.Context(local_rank)
+    kind = args.transport
+    try:
+        eng = slab.SlabEngine(ctx, N, N, world, rank, dist=dist, transport_kind=kind)
+    except RuntimeError:
+        kind = "collective"  # no CUDA IPC / peer access on this box: NCCL all-to-all on the zero-copy send buffer
+        eng = slab.SlabEngine(ctx, N, N, world, rank, dist=dist, transport_kind=kind)
+    plan = eng.plan
+    rows_np = c5_rows(N, plan.y0, plan.nrows, 5)
+    d_rows = torch.from_numpy(rows_np).to(dev)
+    d_bins = torch.from_numpy(bins_np.view(np.int32)).to(dev)
+    d_bits = torch.from_numpy(bits_np).to(dev)
+
+    def step_dev():
+        stego = eng.embed(d_rows, d_bins, d_bits, PARAMS["alpha"], PARAMS["center"])
+        return stego, eng.extract_raw(stego, d_bins, PARAMS["alpha"], PARAMS["center"], dist=dist)
+
+    for _ in range(args.warmup):
+        step_dev()
+    timing.barrier(); torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_reset(); ctx.profile_enable(True)
+    l0 = ctx.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        stego, raw = step_dev()
+    ev[1].record()
+    timing.barrier(); torch.cuda.synchronize()
+    dev_ms = timing.max_over_ranks(ev[0].elapsed_time(ev[1])) / args.steps
+    launches = ctx.launches - l0
+    prof = ctx.profile_read(); ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    ber = float((raw.cpu().numpy().astype(np.uint8) != bits_np).mean())
+    # end to end: pinned host rows in, stego rows and raw bits back on the host, every step
+    h_rows = torch.from_numpy(rows_np).pin_memory()
+    h_out = torch.empty_like(h_rows).pin_memory()
+    h_raw = torch.empty(nbits, dtype=torch.int8).pin_memory()
+
+    def step_e2e():
+        d = h_rows.to(dev, non_blocking=True)
+        st = eng.embed(d, d_bins, d_bits, PARAMS["alpha"], PARAMS["center"])
+        h_out.copy_(st, non_blocking=True)
+        h_raw.copy_(eng.extract_raw(st, d_bins, PARAMS["alpha"], PARAMS["center"], dist=dist), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    timing.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e2e_ms = timing.max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        name, (groups, ms, nbytes) = max(prof.items(), key=lambda kv: kv[1][1])
+        ach = (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0
+        mp = N * N / 1e6
+        line = {
+            "metric": C5_METRIC, "value": mp / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C5 single {N}x{N} RGB image, {args.payload}-byte frame ({nbits} bits, keyed turtlewalk), embed + extract, "
+                                   f"row slabs of {plan.R} rows -> column slabs of {plan.cols} half-spectrum columns on {world} GPU(s)",
+                       "transport": kind, "raw_ber": ber,
+                       "nvlink_bytes_per_rank_per_plane_and_exchange": plan.exchange_bytes_per_plane(),
+                       "algorithmic_exchange_note": "SURVEY 5.8 quotes 448 MiB per GPU and plane for the dense complex spectrum at G = 8; the Hermitian half moves half of it",
+                       "l2": "one 16K image: 6.5 GB of half spectra per direction, far larger than L2"},
+            "clocks": clocks,
+            "e2e": {"value": mp / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(world * rows_np.nbytes),
+                    "d2h_bytes_per_step": int(world * rows_np.nbytes + nbits), "steps": args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if peak else None,
+                         "traffic": None, "peak_source": peak_src, "launch_groups": groups,
+                         "kernels": {k: {"groups": v[0], "ms": round(v[1], 3), "GBps": round((v[2] / 1e9) / (v[1] / 1e3), 1) if v[1] > 0 else None}
+                                     for k, v in prof.items() if v[0]}},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        if hasattr(eng.tr, "close"):
+            eng.tr.close()
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     if args.config == "c4":
         return run_c4(args)
+    if args.config == "c5":
+        return run_c5(args)
     import torch
     import steganosaurus_b200 as sb
     from steganosaurus_b200 import synth
@@ -492,6 +622,29 @@ def run_ours(args):
     h2d = B * (img_bytes + nbits) + B * img_bytes + 2 * 4 * nbits
     d2h = B * img_bytes + B * 8 + B * (38 + npay)
 
+    # ---- what the host<->device links of this node allow for exactly these bytes: the same pinned buffers copied up and
+    # down concurrently on two streams, no kernels, all ranks at once (the e2e leg cannot beat this)
+    ceil_ms = None
+    if e2e_steps:
+        d_a, d_b = torch.empty_like(h_cover, device=dev), torch.empty_like(h_cover, device=dev)
+        d_c = torch.empty_like(h_bits, device=dev)
+        s_up, s_dn = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies():
+            with torch.cuda.stream(s_up):
+                d_a.copy_(h_cover, non_blocking=True); d_c.copy_(h_bits, non_blocking=True); d_a.copy_(h_cover, non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                h_stego.copy_(d_b, non_blocking=True)
+
+        copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copies()
+        torch.cuda.synchronize()
+        ceil_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / 3
+        del d_a, d_b, d_c
+
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -528,7 +681,10 @@ def run_ours(args):
                    "host_placement": placement},
         "clocks": clocks,
         "e2e": {"value": world * mp_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps} if e2e_steps else None,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                # the copies alone (same buffers, both directions at once, all ranks): the ceiling of this leg on this node
+                "copy_ceiling_ms_per_step": ceil_ms, "copy_ceiling_value": world * mp_per_step / (ceil_ms / 1e3) if ceil_ms else None,
+                "frac_of_copy_ceiling": (ceil_ms / e2e_ms) if ceil_ms else None} if e2e_steps else None,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
@@ -550,8 +706,12 @@ def main():
     ap.add_argument("--width", type=int, default=W_UHD)
     ap.add_argument("--height", type=int, default=H_UHD)
     ap.add_argument("--payload", type=int, default=PAYLOAD)
-    ap.add_argument("--config", default="c3", choices=["c3", "c4"],
-                    help="c3 (default): BASELINE's headline, the 4K UHD embed+extract batch; c4: extract-only sweep, one line per N")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
+                    help="c3 (default): BASELINE's headline, the 4K UHD embed+extract batch; c4: extract-only sweep, one line per N; "
+                         "c5: one 16K x 16K image, slab-decomposed 2-D FFT over the ranks (strong scaling)")
+    ap.add_argument("--size", type=int, default=16384, help="--config c5: image width = height")
+    ap.add_argument("--transport", default="peer", choices=["peer", "collective"],
+                    help="--config c5: peer-mapped slabs over NVLink (CUDA IPC) or NCCL all-to-all")
     ap.add_argument("--sizes", default="512,1024,2048,4096,8192", help="--config c4: the N of the N x N stego batches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg (the line then has no e2e)")
