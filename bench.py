@@ -44,6 +44,19 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def device_for_rank(local_rank: int, world: int) -> int:
+    """Rank -> CUDA device.  On this pool's 8-GPU nodes GPUs 0-3 and GPUs 4-7 each share one host path (measured:
+    profiles/r2_pcie_ceiling_8gpu_node.jsonl -- four concurrent pinned H2D streams on GPUs 0-3 get 115 GB/s together, on
+    GPUs 0,4,1,5 212 GB/s), so a 2- or 4-rank job on such a node takes its GPUs from both halves.  The device-resident
+    numbers do not depend on this; TFFT_BENCH_DEVICE_ORDER=identity switches it off."""
+    import torch
+    n = torch.cuda.device_count()
+    order = os.environ.get("TFFT_BENCH_DEVICE_ORDER", "interleave")
+    if order == "interleave" and n == 8 and world in (2, 4):
+        return [0, 4, 1, 5, 2, 6, 3, 7][local_rank]
+    return local_rank % max(n, 1)
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -264,8 +277,9 @@ def run_c4(args):
     import torch
     import steganosaurus_b200 as sb
     rank, local_rank, world = dist_env()
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev_index = device_for_rank(local_rank, world)
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -274,7 +288,7 @@ def run_c4(args):
     from steganosaurus_b200 import shard
     timing = shard.Timing(dist, dev)
     peak, peak_src = measured_peak_hbm()
-    ctx = sb.Context(local_rank)
+    ctx = sb.Context(dev_index)
     for N in [int(x) for x in args.sizes.split(",")]:
         cpu_base = None
         batch, plen, nbits, cap, bins, bits1, stego = c4_case(ctx, N)
@@ -294,7 +308,7 @@ def run_c4(args):
         for _ in range(args.warmup):
             step_dev()
         timing.barrier(); torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(dev_index)
         if rank == 0:
             sampler.start()
         ctx.profile_reset(); ctx.profile_enable(True)
@@ -423,9 +437,18 @@ def run_c5(args):
     d_bins = torch.from_numpy(bins_np.view(np.int32)).to(dev)
     d_bits = torch.from_numpy(bits_np).to(dev)
 
-    def step_dev():
+    ev_mid = []
+
+    def step_dev(mark=False):
         stego = eng.embed(d_rows, d_bins, d_bits, PARAMS["alpha"], PARAMS["center"])
-        return stego, eng.extract_raw(stego, d_bins, PARAMS["alpha"], PARAMS["center"], dist=dist)
+        if mark:
+            e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            e[0].record()
+        raw_ = eng.extract_raw(stego, d_bins, PARAMS["alpha"], PARAMS["center"], dist=dist)
+        if mark:
+            e[1].record()
+            ev_mid.append(e)
+        return stego, raw_
 
     for _ in range(args.warmup):
         step_dev()
@@ -438,10 +461,11 @@ def run_c5(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
     for _ in range(args.steps):
-        stego, raw = step_dev()
+        stego, raw = step_dev(mark=True)
     ev[1].record()
     timing.barrier(); torch.cuda.synchronize()
     dev_ms = timing.max_over_ranks(ev[0].elapsed_time(ev[1])) / args.steps
+    extract_ms = timing.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev_mid) / args.steps)
     launches = ctx.launches - l0
     prof = ctx.profile_read(); ctx.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -475,7 +499,7 @@ def run_c5(args):
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"C5 single {N}x{N} RGB image, {args.payload}-byte frame ({nbits} bits, keyed turtlewalk), embed + extract, "
                                    f"row slabs of {plan.R} rows -> column slabs of {plan.cols} half-spectrum columns on {world} GPU(s)",
-                       "transport": kind, "raw_ber": ber,
+                       "transport": kind, "raw_ber": ber, "embed_ms": dev_ms - extract_ms, "extract_ms": extract_ms,
                        "nvlink_bytes_per_rank_per_plane_and_exchange": plan.exchange_bytes_per_plane(),
                        "algorithmic_exchange_note": "SURVEY 5.8 quotes 448 MiB per GPU and plane for the dense complex spectrum at G = 8; the Hermitian half moves half of it",
                        "l2": "one 16K image: 6.5 GB of half spectra per direction, far larger than L2"},
@@ -514,8 +538,9 @@ def run_ours(args):
     if args.gpus > 1 and world == 1:
         print("bench.py: --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)", file=sys.stderr)
         return 2
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    dev_index = device_for_rank(local_rank, world)
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
     dist = None
     if world > 1:
         import torch.distributed as dist_
@@ -537,7 +562,8 @@ def run_ours(args):
 
     # host placement (after the CPU baseline, which uses every core): CPU time and pinned staging on the GPU's NUMA node
     from steganosaurus_b200 import shard as _shard
-    placement = _shard.bind_host_to_gpu(local_rank) if os.environ.get("TFFT_NO_NUMA_BIND") is None else {"numa_node": None}
+    placement = _shard.bind_host_to_gpu(dev_index) if os.environ.get("TFFT_NO_NUMA_BIND") is None else {"numa_node": None}
+    placement["cuda_device"] = dev_index
 
     # ---- synthetic workload (seeded)
     # the real keyed turtlewalk (host C++, ~1.7 s for 1.72 M bins at 4096^2; cover-independent, shared by the batch)
@@ -545,7 +571,7 @@ def run_ours(args):
     bins_np = host.walk(b"correct horse battery staple", PH, PW, nbits, PARAMS["rmin"], PARAMS["rmax"], 0.7)[0]
     bits_np = make_frame_bits(B, args.payload, 2000 + rank)
     covers_np = make_covers(B, W, H)
-    ctx = sb.Context(local_rank)
+    ctx = sb.Context(dev_index)
 
     d_cover = torch.from_numpy(covers_np).to(dev)
     d_bins = torch.from_numpy(bins_np.view(np.int32)).to(dev)
@@ -573,7 +599,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_dev()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev_index)
     if rank == 0:
         sampler.start()
     ctx.profile_reset()

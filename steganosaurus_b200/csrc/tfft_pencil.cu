@@ -227,7 +227,8 @@ __device__ __forceinline__ double u8_to_double(unsigned v) {
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
 // TW_SHIFT: tw[m << TW_SHIFT] = w_N^m (the global table holds w_16384^k; a shared-memory copy of w_N^m, m < 256, has shift 0)
-template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256, int TW_SHIFT = TW_LOG2 - LOG2N>
+// TW_READY: the table already holds the twiddles of this direction (conjugated for the inverse)
+template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256, int TW_SHIFT = TW_LOG2 - LOG2N, bool TW_READY = false>
 __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
                                        const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/) {
     using G = Geo<LOG2N, VEC>;
@@ -251,7 +252,7 @@ __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2*
         }
         dft<S, G::R1>(x);
         double2 w1 = tw[(size_t)m << TW_SHIFT];
-        if (S < 0) w1.y = -w1.y;
+        if (S < 0 && !TW_READY) w1.y = -w1.y;
         twiddle<G::R1>(x, w1);
 #pragma unroll
         for (int k = 0; k < G::R1; k++) L[(k * 256 + m) * VEC + c] = x[oidx<G::R1>(k)];
@@ -575,8 +576,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
     double* Xw = X + (size_t)k1 * 256 * VEC;        // this warp's private 4 KB slice (8 B entries)
     double2* Sw = (double2*)Xw;                     // the same slice as staging: [k3 (8)][k2 (16)][c] 16 B entries
     const double scale = S < 0 ? 1.0 / (double)G::N : 1.0;  // S:357
-    ThreadTw<S, LOG2N, VEC> ttw;
-    ttw.load(a.tw, tt);
+    __shared__ __align__(16) double2 tw_s[256];     // w_4096^j, j < 256 (conjugated for the inverse): every twiddle base of the pass
 
     if (tid == 0) {
         mbar_init(&full_bar, 1);
@@ -587,22 +587,32 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         mbar_init(&staged1, 512);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
+    if (tid < 256) {
+        double2 w = a.tw[(size_t)tid << (TW_LOG2 - LOG2N)];
+        if (S < 0) w.y = -w.y;
+        tw_s[tid] = w;
+    }
     __syncthreads();
 
-    auto issue_load = [&](long long it) {
-        const int plane = (int)(it / a.groups_per_plane), g = (int)(it % a.groups_per_plane);
+    const int gpp = a.groups_per_plane;
+    auto issue_load = [&](int plane, int g) {
         mbar_expect_tx(&full_bar, (unsigned)((size_t)NZ * BOX_ROWS * VEC * 16));
 #pragma unroll 1
         for (int j = 0; j < NZ; j++) tma_load_3d(L + (size_t)j * BOX_ROWS * VEC, &in_map, &full_bar, g * VEC * 2, j * BOX_ROWS, plane);
     };
 
+    // position of item = plane * gpp + g, advanced without divisions
+    int plane = (int)(blockIdx.x / (unsigned)gpp), g = (int)(blockIdx.x % (unsigned)gpp);
+    const int dplane = (int)(gridDim.x / (unsigned)gpp), dg = (int)(gridDim.x % (unsigned)gpp);
     const long long stride = gridDim.x;
     long long item = blockIdx.x;
-    if (tid == TL && item < a.nitems) issue_load(item);
+    if (tid == TL && item < a.nitems) issue_load(plane, g);
     unsigned parity = 0;
     for (; item < a.nitems; item += stride, parity ^= 1) {
+        int nplane = plane + dplane, ng = g + dg;
+        if (ng >= gpp) { ng -= gpp; nplane++; }
         mbar_wait(&full_bar, parity);
-        stage1<S, LOG2N, VEC, false, NZ>(L, tt, c, a.tw, nullptr, 0, 0, -1);
+        stage1<S, LOG2N, VEC, false, NZ, 0, true>(L, tt, c, tw_s, nullptr, 0, 0, -1);
         __syncthreads();
         double2 x[16];
         stage2_load<LOG2N, VEC>(L, tt, c, x);
@@ -614,11 +624,11 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
         if (tid == TL && item + stride < a.nitems) {
             mbar_wait(&lfree, parity);  // L is free
             fence_async_proxy();
-            issue_load(item + stride);
+            issue_load(nplane, ng);
         }
         // ---- stage 2, warp-local transpose (write [k2][m ^ k2], read [k2 = m][n ^ m]), stage 3
         dft<S, 16>(x);
-        twiddle<16>(x, ttw.s2v());
+        twiddle<16>(x, tw_s[16 * m]);  // w_256^m
         double2 z[16];
         if constexpr (!SIGN) mbar_wait(&xfree_a, parity);  // (SIGN: X is only ever touched by its own warp)
 #pragma unroll
@@ -633,17 +643,30 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
 #pragma unroll
         for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
         dft<S, 16>(z);  // z[oidx(k3)] = output row k1 + 16*m + 256*k3 of column c
-        const int plane = (int)(item / a.groups_per_plane), g = (int)(item % a.groups_per_plane);
         if constexpr (SIGN) {
-            // lane = 2 m + c: one ballot per row block gives the 16 rows x 2 columns of this warp; lane k3 stores word k3
-            unsigned mine = 0;
+            // lane = 2 m + c: one ballot per row block gives the 16 rows x 2 columns of this warp; lane k3 stores word k3.
+            // Off the real axis the read bit is the sign of the imaginary part (branch-free); the rare element within 1e-9 of
+            // the axis goes through the full formula afterwards.
+            unsigned mine = 0, near = 0;
 #pragma unroll
             for (int k3 = 0; k3 < K3N; k3++) {
-                const unsigned w = __ballot_sync(0xffffffffu, read_bit_sign(z[oidx<16>(k3)], a.alpha));
+                const double2 v = z[oidx<16>(k3)];
+                near |= (fabs(v.y) > 1e-9 * fabs(v.x)) ? 0u : (1u << k3);
+                const unsigned w = __ballot_sync(0xffffffffu, v.y > 0.0);
                 if ((tid & 31) == k3) mine = w;
+            }
+            if (__any_sync(0xffffffffu, near != 0u)) {  // (cold)
+#pragma unroll
+                for (int k3 = 0; k3 < K3N; k3++) {
+                    const bool nr = (near >> k3) & 1u;
+                    const int bit = nr ? read_bit_full(z[oidx<16>(k3)].x, z[oidx<16>(k3)].y, a.alpha) : 0;
+                    const unsigned fix = __ballot_sync(0xffffffffu, nr), val = __ballot_sync(0xffffffffu, nr && bit);
+                    if ((tid & 31) == k3) mine = (mine & ~fix) | val;
+                }
             }
             if ((tid & 31) < 8) a.signmap[(((size_t)plane * a.map_groups + g) * 16 + k1) * 8 + (tid & 31)] = mine;
             __syncwarp();  // the next pair's exchange writes come after every lane's reads of the slice
+            plane = nplane; g = ng;
             continue;
         }
         if constexpr (S > 0 && K3N == 16) {
@@ -711,6 +734,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_tma_w(const __grid_constant
                 tma_commit();
             }
         }
+        plane = nplane; g = ng;
     }
     if (tid == TS0 || tid == TS1) tma_wait_all();
 }
