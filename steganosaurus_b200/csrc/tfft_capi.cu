@@ -733,7 +733,7 @@ int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, in
             plan.fused = ctx->h_win[0] == 0;
             plan.k3max = (int)(ctx->h_win[1] >> 8);
             if (plan.fused) {
-                if ((rc = ensure(ctx, ctx->pres, embed_mask_bytes(g.ld, 3)))) return rc;
+                if ((rc = ensure(ctx, ctx->pres, embed_pres_bytes(g.ld)))) return rc;
                 CK(launch_embed_pres(L, d_bins, nbits, g.lay(), (uint16_t*)ctx->pres.p));
             }
         }
@@ -770,7 +770,7 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
     if (plan.fused && nbits) {  // bin-presence masks of the fused pass: once per call, read by every slot stream
-        if ((rc = ensure(ctx, ctx->pres, embed_mask_bytes(g.ld, 3)))) return rc;
+        if ((rc = ensure(ctx, ctx->pres, embed_pres_bytes(g.ld)))) return rc;
         CK(launch_embed_pres(make_launcher(ctx, ctx->slot[0].stream), (const uint32_t*)ctx->bins.p, nbits, g.lay(), (uint16_t*)ctx->pres.p));
         CK(cudaStreamSynchronize(ctx->slot[0].stream));
     }

@@ -1398,13 +1398,23 @@ cudaError_t launch_embed_bins_check(const Launcher& L, const uint32_t* bins, siz
     TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }
+// per (plane % 3, column pair): does any thread of the pair hold a bin?  Pairs without bins skip the phase write, the inverse
+// transform and the store of the column-resident pass (their columns come back unchanged).  [3 * groups] bytes behind pres.
+__global__ void __launch_bounds__(256) embed_pair_flags(const uint32_t* __restrict__ pres32, uint8_t* __restrict__ flags) {
+    const uint32_t w = pres32[(size_t)blockIdx.x * 256 + threadIdx.x];
+    const int any = __syncthreads_or(w != 0u);
+    if (threadIdx.x == 0) flags[blockIdx.x] = any ? 1 : 0;
+}
 size_t embed_mask_bytes(int ld, int nplanes) { return (size_t)nplanes * (ld / 2) * 512 * sizeof(uint16_t); }
+size_t embed_pres_bytes(int ld) { return embed_mask_bytes(ld, 3) + (size_t)3 * (ld / 2); }  // masks + pair flags
 cudaError_t launch_embed_pres(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, uint16_t* pres) {
-    cudaError_t e = cudaMemsetAsync(pres, 0, embed_mask_bytes(lay.ld, 3), L.stream);
+    cudaError_t e = cudaMemsetAsync(pres, 0, embed_pres_bytes(lay.ld), L.stream);
     if (e != cudaSuccess || nbits == 0) return e;
     int lw = 0;
     while ((1 << lw) < lay.PW) lw++;
     embed_pres_build<<<(unsigned)((nbits + 255) / 256), 256, 0, L.stream>>>(bins, nbits, lw, lay.ld / 2, (uint32_t*)pres);
+    TFFT_LAUNCH_CHECK(L);
+    embed_pair_flags<<<(unsigned)(3 * (lay.ld / 2)), 256, 0, L.stream>>>((const uint32_t*)pres, (uint8_t*)pres + embed_mask_bytes(lay.ld, 3));
     TFFT_LAUNCH_CHECK(L);
     return cudaSuccess;
 }

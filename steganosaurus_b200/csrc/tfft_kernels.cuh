@@ -63,7 +63,7 @@ struct PassArgs {
     // exact double, layout of q32) next to the sample.  embed_pres [3][ld/2][512] / embed_val [nplanes][ld/2][512]: per
     // thread and column pair, bit k3 = a bin at row k1 + 16 m + 256 k3 / the bit to write there (embed_masks_* below).
     int fused_embed;
-    const uint16_t* embed_pres;
+    const uint16_t* embed_pres;   // (followed by the pair flags, embed_pres_bytes)
     const uint16_t* embed_val;
     int embed_k3max;
     double embed_cos, embed_sin;
@@ -132,6 +132,7 @@ cudaError_t launch_median_capacity(const Launcher& L, const double2* spec, int n
 
 // ---- column-resident embed (pencil_col_embed_w): bin masks, bin-list check, capacity pass-through ------------------
 size_t embed_mask_bytes(int ld, int nplanes);  // bytes of a [nplanes][ld/2][512] uint16 mask array
+size_t embed_pres_bytes(int ld);               // pres masks [3][ld/2][512] + per-pair "holds a bin" flags [3][ld/2] behind them
 cudaError_t launch_embed_pres(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, uint16_t* pres /*[3][ld/2][512]*/);
 cudaError_t launch_embed_val(const Launcher& L, const uint32_t* bins, const uint8_t* bits, size_t nbits, int nimg, SpecLayout lay,
                              uint16_t* val /*[nimg*3][ld/2][512]*/);

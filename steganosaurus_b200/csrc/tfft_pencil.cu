@@ -770,6 +770,7 @@ struct ColEmbedArgs {
     int sample_groups;
     uint32_t* qhi;         // [plane][g][k1][j][lane] uint4: top words of q for rows k1 + 16 m + 256 (4 j + 0..3), lane = 2 m + c
     uint32_t* qlo;         // the low words, same layout
+    const uint8_t* pair_has_bins;  // [plane % 3][g]: some thread of the pair holds a bin (else: forward + q only)
     const uint16_t* pres;  // [plane % 3][g][tid]   bit k3: a bin at (row k1 + 16 m + 256 k3, column 2 g + c)
     const uint16_t* val;   // [plane][g][tid]       the bits to write there
     int k3max;             // largest row block that holds a bin
@@ -844,12 +845,13 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
     const long long stride = gridDim.x;
     long long item = blockIdx.x;
     if (tid == TL && item < a.nitems) issue_load(plane, g);
-    unsigned parity = 0;
+    unsigned parity = 0, par_st = 0;  // par_st: phase of the store hand-offs (they only advance for pairs that are stored)
     for (; item < a.nitems; item += stride, parity ^= 1) {
         int nplane = plane + dplane, ng = g + dg;
         if (ng >= gpp) { ng -= gpp; nplane++; }
         // this pair's bin masks: 4-byte async copies straight to shared memory (no registers held across the forward pass);
         // completed before the barrier below, read at the phase write
+        const bool has_bins = a.pres != nullptr && a.pair_has_bins[(plane % 3) * gpp + g] != 0;  // (uniform; used after the forward pass)
         if (a.pres) {
             const uint32_t* src = tid < 256 ? (const uint32_t*)a.pres + ((size_t)(plane % 3) * gpp + g) * 256 + tid
                                             : (const uint32_t*)a.val + ((size_t)plane * gpp + g) * 256 + (tid - 256);
@@ -911,8 +913,19 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
             }
             if (samp) a.sample_q[(size_t)plane * a.sample_stride + (size_t)g * 256 + tt] = qs;
         }
+        // A pair without bins comes back from the inverse pass as it went in (up to rounding): leave its columns alone.
+        // (uniform per CTA; with no bins at all -- a capacity-only call -- every pair takes this exit)
+        if (!has_bins) {
+            if (!EARLY_PREFETCH && tid == TL && item + stride < a.nitems) {
+                mbar_wait(&lfree, parity);  // every thread has its stage-2 inputs: L is free
+                fence_async_proxy();
+                issue_load(nplane, ng);
+            }
+            plane = nplane; g = ng;
+            continue;
+        }
         // ================= phase write (write_bit_on_bin S:712-732) on the registers that own the bins =================
-        if (a.pres) {
+        {
             const unsigned pres = (s_pres[tt] >> (16 * c)) & 0xFFFFu, val = s_val[tt] >> (16 * c);
             if (__any_sync(0xffffffffu, pres != 0u)) {
 #pragma unroll
@@ -990,7 +1003,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
         fence_async_proxy();
         mbar_arrive(&staged0);
         if (tid == TS0) {
-            mbar_wait(&staged0, parity);
+            mbar_wait(&staged0, par_st);
             tma_store_5d(&out_map, X, g * VEC * 2, 0, 0, 0, plane);
             if constexpr (K3N > 8 && ONE_ROUND) tma_store_5d(&out_map2, X2, g * VEC * 2, 0, 8, 0, plane);
             tma_commit();
@@ -1000,7 +1013,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
             }
         }
         if constexpr (K3N > 8 && !ONE_ROUND) {
-            mbar_wait(&xfree_b, parity);
+            mbar_wait(&xfree_b, par_st);
 #pragma unroll
             for (int k3 = 8; k3 < 16; k3++) {
                 if (k3 >= K3N) continue;
@@ -1011,11 +1024,12 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
             fence_async_proxy();
             mbar_arrive(&staged1);
             if (tid == TS1) {
-                mbar_wait(&staged1, parity);
+                mbar_wait(&staged1, par_st);
                 tma_store_5d(&out_map, X, g * VEC * 2, 0, 8, 0, plane);
                 tma_commit();
             }
         }
+        par_st ^= 1;
         plane = nplane; g = ng;
     }
     if (tid == TS0 || tid == TS1) tma_wait_all();
@@ -1691,6 +1705,7 @@ cudaError_t run_col_embed_w(const Launcher& L, const PassArgs& p, bool* ok) {
     a.sample_q = p.sample_q; a.sample_stride = p.sample_stride;
     a.sample_groups = (int)(p.sample_stride ? (p.PW - 16) / 2 : 0);  // p.PW is ld = PW_full/2 + 16: pairs below the Nyquist column
     a.qhi = p.qhi; a.qlo = p.qlo; a.pres = p.embed_pres; a.val = p.embed_val; a.k3max = p.embed_k3max;
+    a.pair_has_bins = p.embed_pres ? (const uint8_t*)p.embed_pres + embed_mask_bytes(p.PW, 3) : nullptr;  // (p.PW is ld here)
     a.cos_a = p.embed_cos; a.sin_a = p.embed_sin;
     const size_t smem = G::L_BYTES + pk::X_EMBED_BYTES;
     auto kern = pk::pencil_col_embed_w<NZ, K3N>;
