@@ -1213,6 +1213,7 @@ struct R2CArgs {
     uint8_t* img_out;
     long long nitems;   // nimg * ceil(H/2) row pairs
     int W, H, PW, PH, ld, center;
+    long long stagger;  // cycles the odd unit of a CTA waits once at start (de-phases the two units)
 };
 
 // ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
@@ -1282,7 +1283,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
     for (size_t i = (size_t)tt * 16; i < 2 * RG::UB; i += (size_t)G::UT * 16) *(uint4*)(Ub + i) = make_uint4(0, 0, 0, 0);
     if (unit & 1) {
         const long long t0 = clock64();
-        while (clock64() - t0 < STAGGER_CYCLES) {}
+        while (clock64() - t0 < a.stagger) {}
     }
     unit_bar(bar_id, G::UT);
     int buf = 0;
@@ -1479,7 +1480,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_inv_c2r
 
     if (unit & 1) {
         const long long t0 = clock64();
-        while (clock64() - t0 < STAGGER_CYCLES) {}
+        while (clock64() - t0 < a.stagger) {}
     }
     if (item < a.nitems) issue_loads(item, 0);
     for (; item < a.nitems; item += stride) {
@@ -1784,6 +1785,7 @@ cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
     a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
     a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
     a.nitems = (long long)(p.nplanes / 3) * (WIDE ? p.H : (p.H + 1) / 2);
+    a.stagger = pk::STAGGER_CYCLES;  // (measured: 0 .. 12000 cycles make no difference to either row kernel, profiles/r2_experiments.txt)
     return p.center ? run_r2c_c<LOG2N, UNITS, INV, true, WIDE>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false, WIDE>(L, a);
 }
 
