@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """BASELINE configs 1, 2 and 4 on one GPU (config 3 is bench.py, config 5 is
-tools/run_c5.py).  Prints one JSON line per case.
+bench.py --config c5).  Prints one JSON line per case.
 
     python tools/run_configs.py c1            # 512x512 PNG through both CLIs (ours and the stock reference), all four ways
     python tools/run_configs.py c2            # 1080p (pad 2048^2) and 2048^2 single-image embed+extract, ~8 KB payload
