@@ -124,7 +124,9 @@ struct Geom {
     int large;         // full-spectrum path for a padded dimension above 4096: unfused conversion + four-step passes
     int col4;          // half-spectrum workspace whose column passes are four-step (PH = 8192 / 16384): needs the scratch batch
     size_t E;          // stored elements per plane = PH*ld
-    SpecLayout lay() const { return SpecLayout{PH, PW, ld, half}; }
+    SpecLayout lay() const { return SpecLayout{PH, PW, ld, half, 0, nullptr}; }
+    // layout of a tall half-spectrum workspace whose column pass stopped after the four-step sub-transforms
+    SpecLayout lay_fs(const double2* tw) const { return SpecLayout{PH, PW, ld, half, PH / 4096, tw}; }
 };
 int make_geom(const tfft_ctx* ctx, int W, int H, Geom& g) {
     if (W <= 0 || H <= 0) return TFFT_E_INVALID;
@@ -276,6 +278,7 @@ struct FwdOpts {
     unsigned sample_stride = 0;
     float* q32 = nullptr;                    // ... and a float copy of |F|^2 of every element
     const BinWindow* win = nullptr;          // extract: part of the workspace the bin list reads
+    bool fs_sub_only = false;                // extract, tall half planes: stop the four-step column pass after its sub-transforms
     uint32_t* signmap = nullptr;             // extract: leave read bits (for this alpha) instead of the column-pass spectrum
     double alpha = 0.0;
 };
@@ -306,6 +309,14 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         if (g.H < g.PH)
             CK(cudaMemset2DAsync(spec + (size_t)g.H * g.ld, (size_t)g.PH * g.ld * sizeof(double2), 0,
                                  (size_t)(g.PH - g.H) * g.ld * sizeof(double2), (size_t)nimg * 3, L.stream));
+        if (o.fs_sub_only) {  // readers combine at their bins (SpecLayout::fs_r): one in-place pass over the columns they touch
+            a.in_rows = g.PH; a.fourstep_sub_only = 1;
+            double ncols = cols;
+            if (win && ctx->use_window && win->cols > 0 && win->cols < g.ld) { a.col_limit = win->cols; ncols = (double)win->cols; }
+            ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD_WIN, (double)nimg * 3.0 * 32.0 * (double)g.PH * ncols);
+            CK(launch_fft_pass(L, a));
+            return TFFT_OK;
+        }
         a.in_rows = g.PH; a.tmp = tmp;
         a.leave_in_tmp = where ? 1 : 0;
         ProfScope ps(ctx, L.stream, TFFT_K_C2C, (double)nimg * 3.0 * 32.0 * (double)g.PH * cols);
@@ -466,8 +477,11 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
         fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha;
     }
     if (ctx->adaptive) fo.win = nullptr;  // the medians (S:1124) need the whole spectrum
+    const bool fs = g.col4 && !ctx->adaptive && ctx->fft_impl == 1;  // tall planes: no combine pass, the readers combine at their bins
+    fo.fs_sub_only = fs;
     int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, fo);
     if (rc) return rc;
+    const SpecLayout lay = fs ? g.lay_fs(ctx->d_tw) : g.lay();
     const double* amed = nullptr;
     if (ctx->adaptive) {
         MedianWork mw;
@@ -489,10 +503,10 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
     }
     ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (16.0 + 4.0));
     if (nhdr == 0) {
-        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
+        CK(launch_extract(L, spec, nimg, lay, d_bins, nbins, rep, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
     } else {
-        CK(launch_extract(L, spec, nimg, g.lay(), d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
-        CK(launch_extract(L, spec, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
+        CK(launch_extract(L, spec, nimg, lay, d_bins, nhdr, 3, d_jitter, alpha, d_out_bytes, d_raw, nbins, amed));
+        CK(launch_extract(L, spec, nimg, lay, d_bins + nhdr, nbins - nhdr, 7, d_jitter ? d_jitter + nhdr : nullptr, alpha,
                           d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins, amed));
     }
     return TFFT_OK;
@@ -574,7 +588,7 @@ bool bins_ok_window(const uint32_t* bins, size_t n, const Geom& g, BinWindow& w)
 // device bin list: reduce on the device, read the two numbers back (one stream synchronisation per call)
 int bins_window_dev(tfft_ctx* ctx, const Launcher& L, const uint32_t* d_bins, size_t nbins, const Geom& g, BinWindow& w) {
     w = BinWindow{};
-    if (!ctx->use_window || nbins == 0 || g.large || g.col4) return TFFT_OK;
+    if (!ctx->use_window || nbins == 0 || g.large) return TFFT_OK;
     CK(launch_bins_window(L, d_bins, nbins, g.lay(), ctx->d_win));
     CK(cudaMemcpyAsync(ctx->h_win, ctx->d_win, 3 * sizeof(unsigned), cudaMemcpyDeviceToHost, L.stream));
     CK(cudaStreamSynchronize(L.stream));

@@ -237,10 +237,24 @@ static cudaError_t launch_fourstep(const Launcher& L, const PassArgs& a) {
     if (a.axis == 0) { s.nplanes = a.nplanes * a.PH; s.PH = M; s.PW = R; }          // every row is an [M][R] matrix
     else             { s.PH = M; s.PW = R * a.PW; }                               // plane [N][PW] seen as [M][R*PW]
     s.ld = s.PW; s.in_rows = M; s.out_rows = M; s.W = s.PW; s.H = s.PH;
+    s.col_limit = 0; s.fourstep_sub_only = 0;
     bool handled = false;
-    cudaError_t e = launch_fft_pass_pencil(L, s, &handled);
+    cudaError_t e = cudaSuccess;
+    if (a.axis == 1 && a.fourstep_sub_only && a.col_limit > 0 && a.col_limit < a.PW) {
+        // only the first col_limit columns are read downstream: in the [M][R * PW] view they are R separate column ranges
+        for (int r = 0; r < R && e == cudaSuccess; r++) {
+            PassArgs sr = s;
+            sr.spec = a.spec + (size_t)r * a.PW;
+            sr.col_limit = a.col_limit;
+            e = launch_fft_pass_pencil(L, sr, &handled);
+            if (e == cudaSuccess && !handled) e = cudaErrorNotSupported;
+        }
+        return e;
+    }
+    e = launch_fft_pass_pencil(L, s, &handled);
     if (e != cudaSuccess) return e;
     if (!handled) return cudaErrorNotSupported;
+    if (a.axis == 1 && a.fourstep_sub_only) return cudaSuccess;
     const long long total = (long long)a.nplanes * a.PH * a.PW / R;
     const unsigned grid = (unsigned)((total + 255) / 256);
     if (R == 2) fourstep_combine<2><<<grid, 256, 0, L.stream>>>(a.spec, a.tmp, a.tw, a.axis, a.PH, a.PW, a.log2n, a.inverse, total);
@@ -252,7 +266,8 @@ static cudaError_t launch_fourstep(const Launcher& L, const PassArgs& a) {
 
 cudaError_t launch_fft_pass(const Launcher& L, const PassArgs& a) {
     if (L.fft_impl != 0) {
-        if (a.log2n > 12 && a.log2n <= 14 && a.tmp && !a.img_in && !a.img_out && !a.half) return launch_fourstep(L, a);
+        if (a.log2n > 12 && a.log2n <= 14 && (a.tmp || (a.fourstep_sub_only && a.axis == 1)) && !a.img_in && !a.img_out && !a.half)
+            return launch_fourstep(L, a);
         bool handled = false;
         cudaError_t e = launch_fft_pass_pencil(L, a, &handled);
         if (e == cudaErrorNotSupported && !a.img_in && !a.img_out && !a.signmap && !a.fused_embed && !a.half) {
@@ -288,10 +303,27 @@ __device__ __forceinline__ int col_weight(const SpecLayout& s, int x) {
     return (x == 0 || x == h) ? 1 : (x < h ? 2 : 0);
 }
 // element (y,x) of the FULL spectrum
+// stored element (y, x) of a plane whose column pass stopped after the four-step sub-transforms (SpecLayout::fs_r)
+__device__ __forceinline__ double2 spec_load_fs(const double2* __restrict__ pl, const SpecLayout& s, int y, int x) {
+    const int M = s.PH / s.fs_r, k = y & (M - 1);
+    int lg = 0;
+    while ((1 << lg) < s.PH) lg++;
+    const double2* p0 = pl + (size_t)s.fs_r * k * s.ld + x;
+    double2 acc = p0[0];
+    for (int r = 1; r < s.fs_r; r++) {
+        const unsigned j = (unsigned)(r * y) << (TW_LOG2 - lg);  // w_PH^{r y} from the table of exp(+2 pi i j / 16384), j < 8192
+        double2 w = s.fs_tw[j & (TW_N / 2 - 1)];
+        if (j & (TW_N / 2)) { w.x = -w.x; w.y = -w.y; }
+        const double2 v = p0[(size_t)r * s.ld];
+        acc.x += v.x * w.x - v.y * w.y;
+        acc.y += v.x * w.y + v.y * w.x;
+    }
+    return acc;
+}
 __device__ __forceinline__ double2 spec_load(const double2* __restrict__ pl, const SpecLayout& s, int y, int x) {
-    if (!s.half || x <= (s.PW >> 1)) return pl[(size_t)y * s.ld + x];
+    if (!s.half || x <= (s.PW >> 1)) return s.fs_r ? spec_load_fs(pl, s, y, x) : pl[(size_t)y * s.ld + x];
     const int cy = (s.PH - y) & (s.PH - 1), cx = s.PW - x;
-    double2 z = pl[(size_t)cy * s.ld + cx];
+    double2 z = s.fs_r ? spec_load_fs(pl, s, cy, cx) : pl[(size_t)cy * s.ld + cx];
     z.y = -z.y;
     return z;
 }

@@ -43,6 +43,7 @@ struct PassArgs {
     // (four-step scheme: strided 4096-point sub-transforms in place, radix-2/4 combine through tmp).
     double2* tmp;
     int leave_in_tmp;  // four-step passes only: skip the copy back, the result stays in tmp (the caller ping-pongs)
+    int fourstep_sub_only;  // four-step column passes only: stop after the in-place sub-transforms (SpecLayout::fs_r readers)
     // Forward 4096-point column pass only (optional): the kernel drops a stratified sample of q = re^2 + im^2 (one
     // element per thread and column pair, as IEEE bit patterns) into sample_q[plane * sample_stride + ...] -- the
     // median bracket is then built from it without a separate gather pass over the spectrum.
@@ -78,8 +79,14 @@ inline unsigned col_pass_samples(int PH, int PW_full, int half) { return (PH == 
 // How a plane's spectrum is stored.  full: [PH][PW], ld = PW.  half (real planes, Hermitian):
 // columns 0..PW/2 only, row stride ld = PW/2 + 16 (pad columns are zero); element (y,x) with
 // x > PW/2 is conj of the stored element ((PH-y)%PH, PW-x).
+// fs_r > 0 (extract of a plane taller than 4096 rows): the column pass stopped after the sub-transforms of its four-step
+// scheme (PH = fs_r * M), so stored row fs_r * k + r holds Y_r[k], the M-point transform of the rows r, r + fs_r, ...;
+// readers evaluate X[y] = sum_r w_PH^{r y} Y_r[y mod M] at the bins they need (spec_load) instead of a combine pass
+// over the whole plane.
 struct SpecLayout {
     int PH, PW, ld, half;
+    int fs_r;
+    const double2* fs_tw;
     __host__ __device__ size_t plane_elems() const { return (size_t)PH * ld; }
 };
 
