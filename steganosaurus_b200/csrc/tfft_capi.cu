@@ -281,6 +281,8 @@ struct FwdOpts {
     bool fs_sub_only = false;                // extract, tall half planes: stop the four-step column pass after its sub-transforms
     uint32_t* signmap = nullptr;             // extract: leave read bits (for this alpha) instead of the column-pass spectrum
     double alpha = 0.0;
+    bool fold = false;                       // extract, 8192-row half planes, with signmap: the row pass takes the first radix-2
+                                             // step of the column transform (PassArgs::fold), the columns run as 4096-point passes
 };
 
 // forward 2-D FFT of `nimg` u8 images into spec (S:912-921 / S:1116-1123)
@@ -301,6 +303,23 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
     a.img_in = d_img;
     a.axis = 0; a.log2n = g.lw; a.inverse = 0;
     a.in_rows = g.H;  // rows >= H are zero padding (S:395)
+    if (o.fold) {
+        // 8192-row half planes of an extract that only needs read bits (the caller checked: sign map conditions, window of at
+        // most 4096 rows): the row pass folds rows y and y + 4096 (first radix-2 step of the column transform), all 8192
+        // stored rows are written, and the column pass is the 4096-row sign-map pass over 2 x 3 planes per image
+        a.fold = 1;
+        { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.PH * cols)); CK(launch_fft_pass(L, a)); }
+        a.fold = 0; a.img_in = nullptr;
+        a.axis = 1; a.log2n = 12; a.PW = g.ld; a.half = 0;
+        a.nplanes = nimg * 6; a.PH = 4096; a.in_rows = 4096;
+        a.out_rows = std::min(2048, (win->rows + 1) / 2);
+        a.col_limit = std::min(g.ld, win->cols);
+        a.signmap = o.signmap; a.sign_alpha = o.alpha;
+        const double ncols = (double)a.col_limit;
+        ProfScope ps(ctx, L.stream, TFFT_K_COL_FWD_WIN, (double)nimg * 3.0 * (16.0 * (double)g.PH * ncols + 2.0 * (double)a.out_rows * ncols / 8.0));
+        CK(launch_fft_pass(L, a));
+        return TFFT_OK;
+    }
     { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
     a.img_in = nullptr;
     a.axis = 1; a.log2n = g.lh;  // in_rows stays H: the row pass left rows >= H unwritten (they are zero)
@@ -476,8 +495,16 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
         if (rc2) return rc2;
         fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha;
     }
+    // 8192-row half planes: the same sign map from two 4096-row column passes per plane, the row pass folds (PassArgs::fold)
+    const bool fold = ctx->use_signmap && !ctx->adaptive && ctx->use_window && !d_jitter && g.col4 && g.half && g.lh == 13 && nbins > 0 &&
+                      win.rows > 0 && win.rows <= 4096 && win.cols > 0 && !win.mirrored && alpha >= 1e-6 && alpha <= 3.14159 && signmap_supported(L);
+    if (fold) {
+        int rc2 = ensure(ctx, S.signmap, (size_t)nimg * 6 * sign_map_words(g.ld) * sizeof(uint32_t));
+        if (rc2) return rc2;
+        fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha; fo.fold = true;
+    }
     if (ctx->adaptive) fo.win = nullptr;  // the medians (S:1124) need the whole spectrum
-    const bool fs = g.col4 && !ctx->adaptive && ctx->fft_impl == 1;  // tall planes: no combine pass, the readers combine at their bins
+    const bool fs = g.col4 && !fold && !ctx->adaptive && ctx->fft_impl == 1;  // tall planes: no combine pass, the readers combine at their bins
     fo.fs_sub_only = fs;
     int rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, d_stego, nimg, g, center, &spec, fo);
     if (rc) return rc;
@@ -490,14 +517,15 @@ int extract_chunk(tfft_ctx* ctx, const Launcher& L, Slot& S, const uint8_t* d_st
         CK(launch_median_capacity(L, spec, nimg * 3, g.lay(), 0.0, 0.0, 0.0, mw, (double*)S.medians.p, nullptr));
         amed = (const double*)S.medians.p;
     }
-    if (sign) {
+    if (sign || fold) {
         const uint32_t* bm = (const uint32_t*)S.signmap.p;
+        const int fd = fold ? 1 : 0;
         ProfScope ps(ctx, L.stream, TFFT_K_EXTRACT, (double)nimg * (double)nbins * (4.0 + 4.0));
         if (nhdr == 0) {
-            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nbins, rep, d_out_bytes, d_raw, nbins));
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nbins, rep, d_out_bytes, d_raw, nbins, fd));
         } else {
-            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nhdr, 3, d_out_bytes, d_raw, nbins));
-            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins));
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins, nhdr, 3, d_out_bytes, d_raw, nbins, fd));
+            CK(launch_extract_signmap(L, bm, g.ld, nimg, g.lay(), d_bins + nhdr, nbins - nhdr, 7, d_out_payload, d_raw ? d_raw + nhdr : nullptr, nbins, fd));
         }
         return TFFT_OK;
     }

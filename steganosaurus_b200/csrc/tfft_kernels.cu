@@ -1534,28 +1534,32 @@ __global__ void __launch_bounds__(256) extract_vote(const double2* __restrict__ 
 }
 
 // ---- the same two kernels reading the sign map the forward column pass of an extract left behind (PassArgs::signmap)
-__device__ __forceinline__ int map_bit(const uint32_t* __restrict__ bm, int groups, int img, int PW, uint32_t b) {
+// fold = 1 (PassArgs::fold): an 8192-row plane was transformed as two 4096-row planes, row y of the spectrum is row y >> 1
+// of map plane 2 * plane + (y & 1)
+__device__ __forceinline__ int map_bit(const uint32_t* __restrict__ bm, int groups, int img, int PW, uint32_t b, int fold) {
     const uint32_t lin = b & 0x3FFFFFFFu;
-    const int y = (int)(lin / (uint32_t)PW), x = (int)(lin % (uint32_t)PW);
-    const size_t plane = (size_t)(img * 3 + (int)(b >> 30));
+    int y = (int)(lin / (uint32_t)PW);
+    const int x = (int)(lin % (uint32_t)PW);
+    size_t plane = (size_t)(img * 3 + (int)(b >> 30));
+    if (fold) { plane = 2 * plane + (size_t)(y & 1); y >>= 1; }
     const uint32_t w = bm[((plane * groups + (x >> 1)) * 16 + (y & 15)) * 8 + (y >> 8)];
     return (int)((w >> ((((y >> 4) & 15) << 1) | (x & 1))) & 1u);
 }
 __global__ void __launch_bounds__(256) extract_raw_map(const uint32_t* __restrict__ bm, int groups, int PW, const uint32_t* __restrict__ bins,
-                                                       size_t nbins, uint8_t* raw_bits, size_t raw_stride) {
+                                                       size_t nbins, uint8_t* raw_bits, size_t raw_stride, int fold) {
     const int img = blockIdx.y;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nbins) return;
-    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)map_bit(bm, groups, img, PW, bins[i]);
+    raw_bits[(size_t)img * raw_stride + i] = (uint8_t)map_bit(bm, groups, img, PW, bins[i], fold);
 }
 __global__ void __launch_bounds__(256) extract_vote_map(const uint32_t* __restrict__ bm, int groups, int PW, const uint32_t* __restrict__ bins,
-                                                        size_t ndec, int rep, uint8_t* out_bytes, size_t nbytes) {
+                                                        size_t ndec, int rep, uint8_t* out_bytes, size_t nbytes, int fold) {
     const int img = blockIdx.y;
     const size_t d = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int bit = 0;
     if (d < ndec) {
         int s = 0;
-        for (int j = 0; j < rep; j++) s += map_bit(bm, groups, img, PW, bins[d * rep + j]);
+        for (int j = 0; j < rep; j++) s += map_bit(bm, groups, img, PW, bins[d * rep + j], fold);
         bit = (s >= rep / 2 + 1) ? 1 : 0;
     }
     const unsigned m = __brev(__ballot_sync(0xffffffffu, bit));
@@ -1564,17 +1568,18 @@ __global__ void __launch_bounds__(256) extract_vote_map(const uint32_t* __restri
     if (lane < 4 && byte0 + lane < nbytes) out_bytes[(size_t)img * nbytes + byte0 + lane] = (uint8_t)(m >> (24 - 8 * lane));
 }
 cudaError_t launch_extract_signmap(const Launcher& L, const uint32_t* signmap, int cols, int nimg, SpecLayout lay,
-                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride) {
+                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride,
+                                   int fold) {
     if (nimg == 0) return cudaSuccess;
     const int groups = cols / 2;
     if (raw_bits && nbins) {
-        extract_raw_map<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, nbins, raw_bits, raw_stride ? raw_stride : nbins);
+        extract_raw_map<<<dim3((unsigned)((nbins + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, nbins, raw_bits, raw_stride ? raw_stride : nbins, fold);
         TFFT_LAUNCH_CHECK(L);
     }
     const size_t ndec = nbins / (size_t)rep;
     const size_t nbytes = (ndec + 7) / 8;
     if (out_bytes && nbytes) {
-        extract_vote_map<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, ndec, rep, out_bytes, nbytes);
+        extract_vote_map<<<dim3((unsigned)((ndec + 255) / 256), (unsigned)nimg), 256, 0, L.stream>>>(signmap, groups, lay.PW, bins, ndec, rep, out_bytes, nbytes, fold);
         TFFT_LAUNCH_CHECK(L);
     }
     return cudaSuccess;

@@ -58,6 +58,11 @@ struct PassArgs {
     // signmap (sign_map_words() uint32 per plane, layout in tfft_pencil.cu); spec rows are NOT written.
     uint32_t* signmap;
     double sign_alpha;
+    // Forward u8 row pass of a half-spectrum workspace with PH = 8192 (axis 0, img_in, H > 4096; extract only): rows y and
+    // y + 4096 leave as A_y = F_y + F_{y+4096} (stored row y) and B_y = (F_y - F_{y+4096}) w_8192^y (stored row y + 4096),
+    // the first radix-2 step of the column transform, so the column pass is two 4096-point passes per plane: the workspace
+    // is then read as 2 * nplanes planes of 4096 rows whose column transforms hold rows 2 y' and 2 y' + 1 of the spectrum.
+    int fold;
     // Column-resident embed (fused_embed = 1; axis 1, 4096-row half planes, in_rows = out_rows = H): forward column pass,
     // phase write (write_bit_on_bin S:712-732) and inverse column pass in one shared-memory residency (pencil_col_embed_w in
     // tfft_pencil.cu).  The spectrum is not stored; q = |F|^2 of every element leaves as two 32-bit planes qhi / qlo (the
@@ -163,7 +168,8 @@ cudaError_t launch_extract(const Launcher& L, const double2* spec, int nimg, Spe
 
 // the same votes from a sign map (PassArgs::signmap) of planes with `cols` stored columns; bins must not need the mirror
 cudaError_t launch_extract_signmap(const Launcher& L, const uint32_t* signmap, int cols, int nimg, SpecLayout lay,
-                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0);
+                                   const uint32_t* bins, size_t nbins, int rep, uint8_t* out_bytes, uint8_t* raw_bits, size_t raw_stride = 0,
+                                   int fold = 0 /* the map is that of a folded 8192-row plane (PassArgs::fold) */);
 
 // window of the workspace a bin list touches: d_out2[0] = 1 + largest stored row, [1] = 1 + largest stored column,
 // [2] = some bin is read through its Hermitian mirror (three unsigned)

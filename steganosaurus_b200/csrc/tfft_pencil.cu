@@ -1216,6 +1216,15 @@ struct R2CArgs {
     long long stagger;  // cycles the odd unit of a CTA waits once at start (de-phases the two units)
 };
 
+// FOLD (forward rows of a plane with PH = 8192 whose column pass only has to serve an extract): the first radix-2 step
+// of the 8192-point COLUMN transform (decimation in frequency) is taken here, where rows y and y + 4096 meet anyway:
+//   A_y[k] = F_y[k] + F_{y+4096}[k]              -> stored row y          column FFT_4096 over y gives F2d[2 y'][k]
+//   B_y[k] = (F_y[k] - F_{y+4096}[k]) w_8192^y   -> stored row y + 4096   column FFT_4096 over y gives F2d[2 y' + 1][k]
+// so the column pass of such a plane is two independent 4096-point passes (the 4096-row kernels, sign map included)
+// instead of a four-step pass.  Narrow rows: the row pair of one transform is (y, y + 4096) instead of (y, y + 1) and
+// the fold happens on the registers that hold the two spectra.  WIDE rows (one 8192-pixel row per transform): the two
+// units of a CTA take rows y and y + 4096 and swap halves of their spectra through shared memory.
+
 // ---- forward: two u8 rows x 3 planes -> 2 x 3 half-spectrum rows ----------------------------
 // Staging of a row pair: each row has its own zero-padded region of RS = 3N + 32 bytes, filled by a FIXED
 // number of 16 B cp.async chunks (source size 0 beyond the row end -> zero fill), so stage 1 reads pixel
@@ -1233,11 +1242,14 @@ struct R2CGeo {
 // z[n] = x[2n] + i*x[2n+1]:  with E/O the spectra of the even/odd samples (the same Hermitian split as the row-pair
 // case), X[k] = E[k] + W^k O[k] and X[N-k] = conj(E[k] - W^k O[k]), W = exp(+2 pi i / 2N), k = 0..N/2, X[N/2] = Z[N/2].
 // The half-spectrum row then has N+1 = 4097 columns (ld = N + 16).
-template <int LOG2N, int UNITS, bool CENTER, bool WIDE = false>
+template <int LOG2N, int UNITS, bool CENTER, bool WIDE = false, bool FOLD = false>
 __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c(R2CArgs a) {
     using G = Geo<LOG2N, 1>;
     using RG = R2CGeo<LOG2N>;
     static_assert(!WIDE || LOG2N == 12, "the wide variant packs an 8192-pixel row into a 4096-point transform");
+    static_assert(!(WIDE && FOLD) || UNITS == 2, "folding wide rows pairs the two units of a CTA");
+    constexpr int FR = 4096;                    // FOLD: distance of the two rows that meet (PH / 2)
+    constexpr bool XF = WIDE && FOLD;           // cross-unit fold
     constexpr int N = G::N, NH = N / 2;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int unit = threadIdx.x / G::UT, tt = threadIdx.x % G::UT;
@@ -1245,10 +1257,13 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
     double2* L = (double2*)base;
     unsigned char* Ub = base + RG::LF_BYTES;            // two row-pair buffers of UB bytes
     const int bar_id = 1 + unit;
-    const long long stride = (long long)gridDim.x * UNITS;
-    long long item = (long long)blockIdx.x * UNITS + unit;
-    const int HP = WIDE ? a.H : (a.H + 1) / 2;  // items (row pairs, or single wide rows) per image
-    const int YS = WIDE ? 1 : 2;                // image rows per item
+    // (cross-unit fold: both units of a CTA walk the same items, unit u takes the row FR * u below)
+    const long long stride = XF ? (long long)gridDim.x : (long long)gridDim.x * UNITS;
+    long long item = XF ? (long long)blockIdx.x : (long long)blockIdx.x * UNITS + unit;
+    const int HP = FOLD ? FR : (WIDE ? a.H : (a.H + 1) / 2);  // items (row pairs, or single wide rows) per image
+    const int YS = (WIDE || FOLD) ? 1 : 2;      // first rows of consecutive items
+    const int Y2 = FOLD ? FR : 1;               // narrow rows: distance of the two rows of a pair
+    const int YU = XF ? unit * FR : 0;
     const size_t row_bytes = (size_t)a.W * 3;
     const int nch = (int)((row_bytes + 15) >> 4) + 1;   // chunks per row: covers every 16 B phase of the row start
     const uintptr_t img_base = (uintptr_t)a.img_in;
@@ -1257,16 +1272,22 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
 
     auto pair_start = [&](long long it) -> uintptr_t {
         const long long img = it / HP;
-        const int y0 = YS * (int)(it % HP);
+        const int y0 = YS * (int)(it % HP) + YU;
         return img_base + ((size_t)img * a.H + y0) * row_bytes;
     };
-    auto pair_rows = [&](long long it) -> int { return (!WIDE && 2 * (int)(it % HP) + 1 < a.H) ? 2 : 1; };
+    // rows of the item that exist: narrow 1 or 2 (the second row of the last pair of an odd H / of a folded pair may be
+    // absent), wide 1 (cross-unit fold: 0 when this unit's row lies below the image)
+    auto pair_rows = [&](long long it) -> int {
+        const int y0 = YS * (int)(it % HP) + YU;
+        if constexpr (WIDE) return y0 < a.H ? 1 : 0;
+        else return y0 + Y2 < a.H ? 2 : 1;
+    };
     auto issue_rows = [&](long long it, int buf) {
         const uintptr_t s0 = pair_start(it);
         const int nrows = pair_rows(it);
 #pragma unroll
         for (int r = 0; r < (WIDE ? 1 : 2); r++) {  // wide: one row of up to 2N pixels fills the whole buffer
-            const uintptr_t start = s0 + (size_t)r * row_bytes;
+            const uintptr_t start = s0 + (size_t)r * Y2 * row_bytes;
             const unsigned char* a0 = (const unsigned char*)(start & ~(uintptr_t)15);
             const int span = r < nrows ? (int)(start & 15) + (int)row_bytes : 0;  // bytes from a0 to the row end; absent row: all zero-fill
             unsigned char* dst = Ub + (size_t)buf * RG::UB + (size_t)r * RG::RS;
@@ -1293,14 +1314,16 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
         unit_bar(bar_id, G::UT);
         if (item + stride < a.nitems) issue_rows(item + stride, buf ^ 1);
         const long long img = item / HP;
-        const int y0 = YS * (int)(item % HP);
+        const int y0 = YS * (int)(item % HP) + YU;
         const int nrows = pair_rows(item);
         const uintptr_t s0 = pair_start(item);
         // shared-space byte addresses of the two real inputs of z[tt] (channel 0): pixel tt of row 0 / row 1, or
         // (wide) pixels 2 tt and 2 tt + 1 of the one row
         const uint8_t* r0 = smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + (s0 & 15) + (size_t)tt * (WIDE ? 6 : 3);
         const uint8_t* r1 = WIDE ? r0 + 3
-                                 : smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + row_bytes) & 15) + (size_t)tt * 3;
+                                 : smem_raw + (size_t)unit * RG::FWD_UNIT + RG::LF_BYTES + (size_t)buf * RG::UB + RG::RS + ((s0 + (size_t)Y2 * row_bytes) & 15) + (size_t)tt * 3;
+        [[maybe_unused]] double2 wy = make_double2(1.0, 0.0);   // FOLD: w_8192^y of this item's first row
+        if constexpr (FOLD) wy = a.tw[(size_t)(y0 & (FR - 1)) << (TW_LOG2 - 13)];
         for (int ch = 0; ch < 3; ch++) {
             // ---- stage 1 on z = row0 + i*row1 (plane split, centre sign, zero pad fused; S:383-398)
             double2 x[16];
@@ -1313,7 +1336,11 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     const unsigned o = (unsigned)((n * 256 + j * G::TP) * (WIDE ? 6 : 3)) + (unsigned)ch;
                     double v0 = u8_to_double(r0[o]), v1 = u8_to_double(r1[o]);
                     if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); pair: x parity == m parity; wide: x = 2n, 2n+1
-                        if (((WIDE ? 0 : m) + y0) & 1) v0 = -v0; else v1 = -v1;
+                        if constexpr (FOLD && !WIDE) {  // rows y0 and y0 + 4096 have the same parity
+                            if ((m + y0) & 1) { v0 = -v0; v1 = -v1; }
+                        } else {
+                            if (((WIDE ? 0 : m) + y0) & 1) v0 = -v0; else v1 = -v1;
+                        }
                     }
                     xj[n] = make_double2(v0, v1);
                 }
@@ -1336,8 +1363,58 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
             if (tt == 0) L[NH] = x[oidx<16>(0)];                                          // Z[0] is its own partner
             unit_bar(bar_id, G::UT);
             double2* out0 = a.spec + (((size_t)img * 3 + ch) * a.PH + y0) * a.ld;
-            double2* out1 = out0 + a.ld;
+            double2* out1 = out0 + (size_t)Y2 * a.ld;
             const double2* Lp = L + NH - tt;
+            if constexpr (XF) {
+                // this unit's half-spectrum row X[0..N] as in the wide case below, but nothing is stored yet: unit 0 keeps X[k]
+                // (k = tt + 256 k3) and parks X[N-k] in the free tail of its L, unit 1 the other way round; after the CTA
+                // barrier each unit holds both rows' values of its columns and stores A (row y) and B (row y + 4096)
+                const double2 wb = a.tw[(size_t)tt << (TW_LOG2 - LOG2N - 1)];
+                double2 keep[8];
+                double2* Sm = L + NH + 1;                                   // 2049 entries, clear of the split's L[0..NH]
+                const double2* So = (const double2*)(smem_raw + (size_t)(unit ^ 1) * RG::FWD_UNIT) + NH + 1;
+#pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) {
+                    constexpr double C32[8] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                                               0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785};
+                    constexpr double S32[8] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913};
+                    const double2 z = x[oidx<16>(k3)];
+                    const double2 zn = Lp[-G::TP * k3];
+                    const double2 E = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));
+                    const double2 O = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));
+                    const double2 w = k3 == 0 ? wb : cmulc<+1>(wb, C32[k3], S32[k3]);
+                    const double2 t = cmul(w, O);
+                    const double2 XK = make_double2(E.x + t.x, E.y + t.y);   // X[k]
+                    const double2 XM = make_double2(E.x - t.x, t.y - E.y);   // X[N-k] = conj(E - t)
+                    keep[k3] = unit == 0 ? XK : XM;
+                    Sm[k3 * G::TP + tt] = unit == 0 ? XM : XK;
+                }
+                if (tt == 0) Sm[8 * G::TP] = x[oidx<16>(8)];                  // X[N/2] = Z[N/2]
+                __syncthreads();
+                const size_t yA = (size_t)(y0 & (FR - 1));
+                double2* rowA = a.spec + (((size_t)img * 3 + ch) * a.PH + yA) * a.ld;
+                double2* rowB = rowA + (size_t)FR * a.ld;
+                const int col0 = unit == 0 ? tt : N - tt, cstep = unit == 0 ? G::TP : -G::TP;
+#pragma unroll
+                for (int k3 = 0; k3 < 8; k3++) {
+                    const double2 o = So[k3 * G::TP + tt];
+                    const double2 X0 = unit == 0 ? keep[k3] : o, X1 = unit == 0 ? o : keep[k3];
+                    rowA[col0 + cstep * k3] = cadd(X0, X1);
+                    rowB[col0 + cstep * k3] = cmul(csub(X0, X1), wy);
+                }
+                if (unit == 0 && tt == 0) {
+                    const double2 X0 = x[oidx<16>(8)], X1 = So[8 * G::TP];
+                    rowA[NH] = cadd(X0, X1);
+                    rowB[NH] = cmul(csub(X0, X1), wy);
+                }
+                if (unit == 0 && tt >= 1 && tt < 16) {                        // pad columns N+1 .. N+15
+                    rowA[N + tt] = make_double2(0.0, 0.0);
+                    rowB[N + tt] = make_double2(0.0, 0.0);
+                }
+                __syncthreads();  // the other unit has read my parked half: the next plane's stage 1 may overwrite L
+                continue;
+            }
             if constexpr (WIDE) {
                 // W^k = W^tt * (W^TP)^k3 with W = exp(2 pi i / 2N): table entry 2 tt, then constant rotations by 2 pi k3 / 32
                 const double2 wb = a.tw[(size_t)tt << (TW_LOG2 - LOG2N - 1)];
@@ -1365,13 +1442,26 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     const int k = tt + G::TP * k3;
                     const double2 z = x[oidx<16>(k3)];
                     const double2 zn = Lp[-G::TP * k3];  // Z[N-k] = L[(N-k) - N/2]; k = 0 reads L[NH] = Z[0]
-                    out0[k] = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));            // (Z[k] + conj Z[N-k]) / 2
-                    if (nrows == 2) out1[k] = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));  // (Z[k] - conj Z[N-k]) / 2i
+                    const double2 F0 = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));   // (Z[k] + conj Z[N-k]) / 2
+                    const double2 F1 = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));   // (Z[k] - conj Z[N-k]) / 2i
+                    if constexpr (FOLD) {  // rows y0 and y0 + 4096 of the plane: A and B (an absent second row is zero)
+                        out0[k] = nrows == 2 ? cadd(F0, F1) : F0;
+                        out1[k] = cmul(nrows == 2 ? csub(F0, F1) : F0, wy);
+                    } else {
+                        out0[k] = F0;
+                        if (nrows == 2) out1[k] = F1;
+                    }
                 }
                 if (tt < 16) {  // Nyquist column (real) and the zero pad columns N/2+1 .. N/2+15
                     const double2 z8 = x[oidx<16>(8)];
-                    out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
-                    if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
+                    if constexpr (FOLD) {
+                        const double f1 = nrows == 2 ? z8.y : 0.0;
+                        out0[NH + tt] = tt == 0 ? make_double2(z8.x + f1, 0.0) : make_double2(0.0, 0.0);
+                        out1[NH + tt] = tt == 0 ? make_double2((z8.x - f1) * wy.x, (z8.x - f1) * wy.y) : make_double2(0.0, 0.0);
+                    } else {
+                        out0[NH + tt] = tt == 0 ? make_double2(z8.x, 0.0) : make_double2(0.0, 0.0);
+                        if (nrows == 2) out1[NH + tt] = tt == 0 ? make_double2(z8.y, 0.0) : make_double2(0.0, 0.0);
+                    }
                 }
             }
             unit_bar(bar_id, G::UT);  // L is rewritten by the next plane's stage 1
@@ -1760,7 +1850,7 @@ cudaError_t run_u8(const Launcher& L, const PassArgs& p) {
     return cudaGetLastError();
 }
 
-template <int LOG2N, int UNITS, bool INV, bool CENTER, bool WIDE>
+template <int LOG2N, int UNITS, bool INV, bool CENTER, bool WIDE, bool FOLD = false>
 cudaError_t run_r2c_c(const Launcher& L, const pk::R2CArgs& a) {
     using G = pk::Geo<LOG2N, 1>;
     const size_t smem = (INV ? pk::C2RGeo<LOG2N>::UNIT : pk::R2CGeo<LOG2N>::FWD_UNIT) * UNITS;
@@ -1770,23 +1860,25 @@ cudaError_t run_r2c_c(const Launcher& L, const pk::R2CArgs& a) {
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
         kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     } else {
-        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS, CENTER, WIDE>;
+        auto kern = pk::pencil_u8_fwd_r2c<LOG2N, UNITS, CENTER, WIDE, FOLD>;
         if ((e = set_smem(kern, smem)) != cudaSuccess) return e;
-        kern<<<grid_for(L, a.nitems, UNITS), G::UT * UNITS, smem, L.stream>>>(a);
+        // (folded wide rows: one item per CTA at a time, its two units take the two rows of the item)
+        kern<<<grid_for(L, a.nitems, (WIDE && FOLD) ? 1 : UNITS), G::UT * UNITS, smem, L.stream>>>(a);
     }
     if (L.launch_counter) ++*L.launch_counter;
     return cudaGetLastError();
 }
 
 // WIDE: p.PW = 8192 runs on the 4096-point kernels (LOG2N = 12), one image row per item
-template <int LOG2N, int UNITS, bool INV, bool WIDE = false>
+// FOLD: PassArgs::fold (forward rows of an 8192-row plane: rows y and y + 4096 leave as A_y and B_y, see R2CArgs)
+template <int LOG2N, int UNITS, bool INV, bool WIDE = false, bool FOLD = false>
 cudaError_t run_r2c(const Launcher& L, const PassArgs& p) {
     pk::R2CArgs a;
     a.spec = p.spec; a.tw = p.tw; a.img_in = p.img_in; a.img_out = p.img_out;
     a.W = p.W; a.H = p.H; a.PW = p.PW; a.PH = p.PH; a.ld = p.ld; a.center = p.center;
-    a.nitems = (long long)(p.nplanes / 3) * (WIDE ? p.H : (p.H + 1) / 2);
+    a.nitems = (long long)(p.nplanes / 3) * (FOLD ? 4096 : (WIDE ? p.H : (p.H + 1) / 2));
     a.stagger = pk::STAGGER_CYCLES;  // (measured: 0 .. 12000 cycles make no difference to either row kernel, profiles/r2_experiments.txt)
-    return p.center ? run_r2c_c<LOG2N, UNITS, INV, true, WIDE>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false, WIDE>(L, a);
+    return p.center ? run_r2c_c<LOG2N, UNITS, INV, true, WIDE, FOLD>(L, a) : run_r2c_c<LOG2N, UNITS, INV, false, WIDE, FOLD>(L, a);
 }
 
 // per-size unit counts: rows: (N*24 B) per unit, columns: VEC so that one unit fills ~192 KB
@@ -1800,6 +1892,10 @@ template <> struct Cfg<9>  { static constexpr int ROW_UNITS = 8, COL_VEC = 4, CO
 template <int LOG2N>
 cudaError_t dispatch(const Launcher& L, const PassArgs& p) {
     using C = Cfg<LOG2N>;
+    if (p.fold) {
+        if (!(p.half && p.img_in && p.PH == 8192 && p.H > 4096)) return cudaErrorNotSupported;
+        return run_r2c<LOG2N, C::U8F_UNITS, false, false, true>(L, p);
+    }
     if (p.half && p.img_in) return run_r2c<LOG2N, C::U8F_UNITS, false>(L, p);
     if (p.half && p.img_out) return run_r2c<LOG2N, C::U8I_UNITS, true>(L, p);
     if (p.img_in) return run_u8<LOG2N, C::U8F_UNITS, false>(L, p);
@@ -1851,6 +1947,7 @@ bool fused_embed_supported(const Launcher& L) { return signmap_supported(L); }
 cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* handled) {
     *handled = true;
     if ((p.signmap || p.fused_embed) && !(p.log2n == 12 && p.axis == 1)) return cudaErrorNotSupported;
+    if (p.fold && (p.axis != 0 || p.log2n < 9 || p.log2n > 13)) return cudaErrorNotSupported;
     // the fused u8 passes need W <= PW == N (always true) and run along x only
     switch (p.log2n) {
         case 12: return dispatch<12>(L, p);
@@ -1858,6 +1955,10 @@ cudaError_t launch_fft_pass_pencil(const Launcher& L, const PassArgs& p, bool* h
         case 10: return dispatch<10>(L, p);
         case 9: return dispatch<9>(L, p);
         case 13:  // 8192-pixel rows of a half-spectrum workspace: packed into the 4096-point fused u8 kernels
+            if (p.fold) {
+                if (!(p.half && p.axis == 0 && p.img_in && p.PH == 8192 && p.H > 4096)) return cudaErrorNotSupported;
+                return run_r2c<12, Cfg<12>::U8F_UNITS, false, true, true>(L, p);
+            }
             if (p.half && p.axis == 0 && p.img_in) return run_r2c<12, Cfg<12>::U8F_UNITS, false, true>(L, p);
             if (p.half && p.axis == 0 && p.img_out) return run_r2c<12, Cfg<12>::U8I_UNITS, true, true>(L, p);
             *handled = false;

@@ -54,13 +54,15 @@ def test_fft2d_known_answer(ctx):
     assert np.allclose(F, np.exp(2j * np.pi * k / 16)[None, :].repeat(16, 0), atol=1e-14)
 
 
-@pytest.mark.parametrize("W,H,center", [(64, 48, False), (100, 60, True), (512, 512, False), (300, 1000, True)])
+@pytest.mark.parametrize("W,H,center", [(64, 48, False), (100, 60, True), (512, 512, False), (300, 1000, True),
+                                        (4000, 520, False), (4096, 513, True), (3840, 600, True)])  # 4096-point row kernels, odd H
 def test_forward_spectrum(ctx, W, H, center):
     img = synth.gen_texture(W, H, W * 7 + H)
     got = ctx.forward_spectrum(img, center)
     want = oracle().forward_spectrum(img, center)
     e = spec_err(got, want)
-    assert e[0] < SPEC_TOL and e[1] < 1e-13, e
+    # (4096-point rows: the oracle's own twiddle recurrence, S:353, carries ~len * eps -- max bar 3e-11 there; north_star 1e-9)
+    assert e[0] < (SPEC_TOL if W <= 2048 else 3e-11) and e[1] < 1e-13, e
     # Hermitian symmetry of a real plane's spectrum
     conj = np.conj(np.roll(np.flip(got, (1, 2)), 1, (1, 2)))
     assert np.abs(got - conj).max() / np.abs(got).max() < 1e-13
