@@ -101,6 +101,13 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
                      const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
                      double alpha, int center, double magmin, double rmin, double rmax,
                      uint8_t* stego, uint64_t* usable, double* median);
+/* The same call with the frame bits packed eight to a byte, MSB first -- the order bits_from_bytes / bytes_from_bits use
+ * (S:447-459): bits_packed = [n][ceil(nbits / 8)], bit i of image j = (bits_packed[j][i / 8] >> (7 - i % 8)) & 1.  One eighth
+ * of the host->device bytes of the bit array (a 4K batch's frame bits are 3 % of an embed+extract step's uploads). */
+int tfft_embed_batch_packed(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                            const uint32_t* bins, const uint8_t* bits_packed, size_t nbits, const double* jitter,
+                            double alpha, int center, double magmin, double rmin, double rmax,
+                            uint8_t* stego, uint64_t* usable, double* median);
 int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, int H,
                          const uint32_t* d_bins, const uint8_t* d_bits, size_t nbits,
                          const double* d_jitter, double alpha, int center, double magmin,

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("TFFT_LIB") or os.path.join(PKG, "libtfft_b200.so")  #
 SYMBOLS = [
     "tfft_create", "tfft_destroy", "tfft_abi_version", "tfft_strerror", "tfft_last_cuda_error",
     "tfft_set_workspace_limit", "tfft_set_adaptive_alpha", "tfft_host_alloc", "tfft_host_free", "tfft_launch_count",
-    "tfft_embed_batch", "tfft_embed_batch_dev", "tfft_extract_bits", "tfft_extract_bits_dev",
+    "tfft_embed_batch", "tfft_embed_batch_packed", "tfft_embed_batch_dev", "tfft_extract_bits", "tfft_extract_bits_dev",
     "tfft_forward_batch", "tfft_read_bits", "tfft_forward_spectrum", "tfft_fft2d", "tfft_fft2d_dev",
     "tfft_fft_pass_dev", "tfft_median_capacity_dev", "tfft_extract_frame", "tfft_extract_frame_dev",
     "tfft_profile_enable", "tfft_profile_reset", "tfft_profile_read", "tfft_kind_name", "tfft_bin_window",
@@ -62,6 +62,8 @@ def load() -> C.CDLL:
     emb = [vp, vp, i, i, i, vp, vp, sz, vp, d, i, d, d, d, vp, vp, vp]
     L.tfft_embed_batch.argtypes = emb
     L.tfft_embed_batch.restype = i
+    L.tfft_embed_batch_packed.argtypes = emb
+    L.tfft_embed_batch_packed.restype = i
     L.tfft_embed_batch_dev.argtypes = emb + [vp]
     L.tfft_embed_batch_dev.restype = i
     ext = [vp, vp, i, i, i, vp, sz, i, vp, d, i, vp, vp]

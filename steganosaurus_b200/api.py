@@ -105,20 +105,23 @@ class Context:
 
     # ------------------------------------------------------------------ host-buffer entry points
     def embed_batch(self, cover, bins, bits, alpha=0.5, center=False, magmin=0.01, rmin=0.05, rmax=0.45,
-                    jitter=None, out=None):
-        """cover u8 [n,H,W,3]; bins u32 [nbits]; bits u8 [n,nbits] -> (stego, usable[n], median[n,3])."""
+                    jitter=None, out=None, packed=False):
+        """cover u8 [n,H,W,3]; bins u32 [nbits]; bits u8 [n,nbits] (packed: [n, ceil(nbits/8)], MSB first as
+        bytes_from_bits S:447) -> (stego, usable[n], median[n,3])."""
         cover = np.ascontiguousarray(cover, np.uint8)
         n, H, W, ch = cover.shape
         assert ch == 3
         bins = np.ascontiguousarray(bins, np.uint32)
-        bits = np.ascontiguousarray(bits, np.uint8).reshape(n, -1) if n else np.zeros((0, bins.size), np.uint8)
-        assert bits.shape[1] == bins.size, "bits must be [n, nbits]"
+        width = (bins.size + 7) // 8 if packed else bins.size
+        bits = np.ascontiguousarray(bits, np.uint8).reshape(n, -1) if n else np.zeros((0, width), np.uint8)
+        assert bits.shape[1] == width, "bits must be [n, nbits] (packed: [n, ceil(nbits / 8)])"
         jit = None if jitter is None else np.ascontiguousarray(jitter, np.float64)
         stego = np.empty_like(cover) if out is None else out
         usable = np.zeros(max(n, 1), np.uint64)
         median = np.zeros((max(n, 1), 3), np.float64)
-        rc = self.L.tfft_embed_batch(self.h, _ptr(cover), n, W, H, _ptr(bins), _ptr(bits), bins.size, _ptr(jit),
-                                     alpha, int(center), magmin, rmin, rmax, _ptr(stego), _ptr(usable), _ptr(median))
+        fn = self.L.tfft_embed_batch_packed if packed else self.L.tfft_embed_batch
+        rc = fn(self.h, _ptr(cover), n, W, H, _ptr(bins), _ptr(bits), bins.size, _ptr(jit),
+                alpha, int(center), magmin, rmin, rmax, _ptr(stego), _ptr(usable), _ptr(median))
         if rc == E_CAPACITY:
             raise CapacityError(bins.size, usable[:n], stego, median[:n])
         self._check(rc)

@@ -28,6 +28,7 @@ struct Slot {
     DevBuf q32;      // embed on 4096-row half planes: float copy of |F|^2 left by the column pass for the median scan
                      // (column-resident embed: the two 32-bit planes of the exact q instead, qhi then qlo)
     DevBuf val;      // column-resident embed: per-image bit masks of the fused pass (embed_val_build)
+    DevBuf bitsp;    // tfft_embed_batch_packed: the chunk's packed frame bits as uploaded
     // pinned staging for the small per-chunk results (capacity verdict, medians, decoded bytes): they
     // are copied to the caller's (possibly pageable) memory only when the chunk is drained, so the
     // asynchronous pipeline never blocks on a pageable cudaMemcpyAsync
@@ -69,6 +70,12 @@ struct tfft_ctx {
     // resident spectra for the two-phase extract
     int res_n = 0, res_PH = 0, res_PW = 0;
     double2* res_spec = nullptr;  // buffer of slot 0 that holds them
+    // 4096-row half planes: tfft_forward_batch stops after the row pass (res_stage 1) and the first tfft_read_bits decides
+    // what the column pass leaves behind -- the sign map of the quarter plane for this alpha (res_stage 2; the row-pass
+    // output stays intact, so a later list outside the map or with jitter can still get the full pass) or the spectrum
+    // (res_stage 0, as for every other geometry)
+    int res_stage = 0, res_W = 0, res_H = 0;
+    double res_alpha = 0.0;
     char cuda_err[256] = {0};
     // per-kernel-kind timing (tfft_profile_*)
     bool prof_on = false;
@@ -281,6 +288,7 @@ struct FwdOpts {
     bool fs_sub_only = false;                // extract, tall half planes: stop the four-step column pass after its sub-transforms
     uint32_t* signmap = nullptr;             // extract: leave read bits (for this alpha) instead of the column-pass spectrum
     double alpha = 0.0;
+    bool rows_only = false, cols_only = false;  // two-phase extract: the row pass now, the column pass when the first bin list arrives
     bool fold = false;                       // extract, 8192-row half planes, with signmap: the row pass takes the first radix-2
                                              // step of the column transform (PassArgs::fold), the columns run as 4096-point passes
 };
@@ -320,7 +328,8 @@ int forward_images(tfft_ctx* ctx, const Launcher& L, double2* spec, double2* tmp
         CK(launch_fft_pass(L, a));
         return TFFT_OK;
     }
-    { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    if (!o.cols_only) { ProfScope ps(ctx, L.stream, TFFT_K_ROW_FWD, (double)nimg * 3.0 * ((double)g.W * g.H + 16.0 * (double)g.H * cols)); CK(launch_fft_pass(L, a)); }
+    if (o.rows_only) return TFFT_OK;
     a.img_in = nullptr;
     a.axis = 1; a.log2n = g.lh;  // in_rows stays H: the row pass left rows >= H unwritten (they are zero)
     if (g.half) { a.PW = g.ld; a.half = 0; }  // the column pass just sees a plane of ld columns
@@ -695,7 +704,7 @@ void tfft_destroy(tfft_ctx* ctx) {
     cudaDeviceSynchronize();
     for (int i = 0; i < NSLOT; i++) {
         Slot& S = ctx->slot[i];
-        release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.med);
+        release(S.spec); release(S.spec2); release(S.in); release(S.out); release(S.bits); release(S.bitsp); release(S.med);
         release(S.medians); release(S.usable); release(S.outbytes); release(S.raw); release(S.signmap); release(S.q32); release(S.val);
         if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.stream) cudaStreamDestroy(S.stream);
@@ -791,11 +800,13 @@ int tfft_embed_batch_dev(tfft_ctx* ctx, const uint8_t* d_cover, int n, int W, in
     return TFFT_OK;
 }
 
-int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
-                     const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
-                     double alpha, int center, double magmin, double rmin, double rmax,
-                     uint8_t* stego, uint64_t* usable, double* median) {
+// packed: bits = [n][ceil(nbits / 8)] MSB first instead of [n][nbits] one bit per byte
+static int embed_host_impl(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                           const uint32_t* bins, const uint8_t* bits, bool packed, size_t nbits, const double* jitter,
+                           double alpha, int center, double magmin, double rmin, double rmax,
+                           uint8_t* stego, uint64_t* usable, double* median) {
     if (!ctx || !cover || !stego || n < 0 || (nbits && (!bins || !bits))) return TFFT_E_INVALID;
+    const size_t pbytes = (nbits + 7) / 8;
     Geom g;
     int rc = make_geom(ctx, W, H, g);
     if (rc) return rc;
@@ -808,8 +819,10 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     plan.fused = fusable && fused_geometry_ok(ctx, make_launcher(ctx, ctx->slot[0].stream), g, jitter);
     const int chunk = std::min(chunk_for(ctx, g, n, HOST_SLOTS), HOST_CHUNK);
     const int nslots = std::min(HOST_SLOTS, (n + chunk - 1) / chunk);
-    for (int s = 0; s < nslots; s++)
+    for (int s = 0; s < nslots; s++) {
         if ((rc = ensure_slot(ctx, ctx->slot[s], g, chunk, true, nbits, 0, 0))) return rc;
+        if (packed && nbits && (rc = ensure(ctx, ctx->slot[s].bitsp, (size_t)chunk * pbytes))) return rc;
+    }
     if ((rc = upload_bins(ctx, bins, nbits, jitter, ctx->slot[0].stream))) return rc;
     if (plan.fused && nbits) {  // bin-presence masks of the fused pass: once per call, read by every slot stream
         if ((rc = ensure(ctx, ctx->pres, embed_pres_bytes(g.ld)))) return rc;
@@ -844,8 +857,13 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
         cudaStream_t st = S.stream;
         if ((rc = drain(sl))) return rc;  // the slot's buffers are about to be reused
         CK(cudaMemcpyAsync(S.in.p, cover + (size_t)i0 * g.img_bytes, (size_t)m * g.img_bytes, cudaMemcpyHostToDevice, st));
-        if (nbits) CK(cudaMemcpyAsync(S.bits.p, bits + (size_t)i0 * nbits, (size_t)m * nbits, cudaMemcpyHostToDevice, st));
         Launcher L = make_launcher(ctx, st);
+        if (nbits && packed) {
+            CK(cudaMemcpyAsync(S.bitsp.p, bits + (size_t)i0 * pbytes, (size_t)m * pbytes, cudaMemcpyHostToDevice, st));
+            CK(launch_unpack_bits(L, (const uint8_t*)S.bitsp.p, pbytes, (uint8_t*)S.bits.p, nbits, m));
+        } else if (nbits) {
+            CK(cudaMemcpyAsync(S.bits.p, bits + (size_t)i0 * nbits, (size_t)m * nbits, cudaMemcpyHostToDevice, st));
+        }
         rc = embed_chunk(ctx, L, S, (const uint8_t*)S.in.p, m, g, (const uint32_t*)ctx->bins.p, (const uint8_t*)S.bits.p, nbits,
                          jitter ? (const double*)ctx->jitter.p : nullptr, alpha, center, magmin, rmin, rmax,
                          (uint8_t*)S.out.p, (uint64_t*)S.usable.p, (double*)S.medians.p, plan);
@@ -858,6 +876,19 @@ int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
     for (int k = 0; k < nslots; k++)  // oldest first
         if ((rc = drain((ci + k) % nslots))) return rc;
     return over ? TFFT_E_CAPACITY : TFFT_OK;
+}
+
+int tfft_embed_batch(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                     const uint32_t* bins, const uint8_t* bits, size_t nbits, const double* jitter,
+                     double alpha, int center, double magmin, double rmin, double rmax,
+                     uint8_t* stego, uint64_t* usable, double* median) {
+    return embed_host_impl(ctx, cover, n, W, H, bins, bits, false, nbits, jitter, alpha, center, magmin, rmin, rmax, stego, usable, median);
+}
+int tfft_embed_batch_packed(tfft_ctx* ctx, const uint8_t* cover, int n, int W, int H,
+                            const uint32_t* bins, const uint8_t* bits_packed, size_t nbits, const double* jitter,
+                            double alpha, int center, double magmin, double rmin, double rmax,
+                            uint8_t* stego, uint64_t* usable, double* median) {
+    return embed_host_impl(ctx, cover, n, W, H, bins, bits_packed, true, nbits, jitter, alpha, center, magmin, rmin, rmax, stego, usable, median);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -976,7 +1007,7 @@ int tfft_extract_frame(tfft_ctx* ctx, const uint8_t* stego, int n, int W, int H,
 }
 
 // ---------------------------------------------------------------------------------------------
-int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center) {
+static int forward_batch_impl(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center, bool eager) {
     if (!ctx || !img || n <= 0) return TFFT_E_INVALID;
     Geom g;
     int rc = make_geom(ctx, W, H, g);
@@ -988,6 +1019,16 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     if ((rc = ensure_slot(ctx, S, g, n, true, 0, 0, 0))) return rc;
     CK(cudaMemcpyAsync(S.in.p, img, (size_t)n * g.img_bytes, cudaMemcpyHostToDevice, S.stream));
     Launcher L = make_launcher(ctx, S.stream);
+    ctx->res_stage = 0; ctx->res_W = W; ctx->res_H = H;
+    if (!eager && ctx->use_signmap && ctx->use_window && !ctx->adaptive && g.half && g.lh == 12 && !g.col4 && !g.large && signmap_supported(L)) {
+        FwdOpts fo;
+        fo.rows_only = true;
+        if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center, nullptr, fo))) return rc;
+        CK(cudaStreamSynchronize(S.stream));
+        ctx->res_spec = (double2*)S.spec.p;
+        ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay(); ctx->res_stage = 1;
+        return TFFT_OK;
+    }
     if ((rc = forward_images(ctx, L, (double2*)S.spec.p, (double2*)S.spec2.p, (const uint8_t*)S.in.p, n, g, center, &ctx->res_spec))) return rc;
     if (ctx->adaptive) {  // S:1124: the medians of the stego spectra scale alpha in read_bit_from_bin
         MedianWork mw;
@@ -997,6 +1038,10 @@ int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, i
     CK(cudaStreamSynchronize(S.stream));
     ctx->res_n = n; ctx->res_PH = g.PH; ctx->res_PW = g.PW; ctx->res_lay = g.lay();
     return TFFT_OK;
+}
+
+int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center) {
+    return forward_batch_impl(ctx, img, n, W, H, center, /*eager=*/false);
 }
 
 int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, const double* jitter,
@@ -1014,6 +1059,36 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
     if (raw_bits && nbins && (rc = ensure(ctx, S.raw, (size_t)n * nbins))) return rc;
     if ((rc = upload_bins(ctx, bins, nbins, jitter, S.stream))) return rc;
     Launcher L = make_launcher(ctx, S.stream);
+    if (ctx->res_stage != 0) {  // the column pass is still owed (or left a sign map): decide on this list
+        Geom g;
+        if ((rc = make_geom(ctx, ctx->res_W, ctx->res_H, g))) return rc;
+        BinWindow win;
+        if (!bins_ok_window(bins, nbins, g, win)) return TFFT_E_INVALID;
+        const bool sign = !jitter && nbins > 0 && win.rows <= 2048 && !win.mirrored && alpha >= 1e-6 && alpha <= 3.14159;
+        if (sign) {
+            if (ctx->res_stage != 2 || ctx->res_alpha != alpha) {  // read bits of the whole quarter plane (rows < 2048), once per alpha
+                if ((rc = ensure(ctx, S.signmap, (size_t)n * 3 * sign_map_words(g.ld) * sizeof(uint32_t)))) return rc;
+                BinWindow q;
+                q.rows = 2048; q.cols = g.ld;
+                FwdOpts fo;
+                fo.cols_only = true; fo.win = &q; fo.signmap = (uint32_t*)S.signmap.p; fo.alpha = alpha;
+                if ((rc = forward_images(ctx, L, ctx->res_spec, (double2*)S.spec2.p, nullptr, n, g, 0, nullptr, fo))) return rc;
+                ctx->res_stage = 2; ctx->res_alpha = alpha;
+            }
+            ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (4.0 + 4.0));
+            CK(launch_extract_signmap(L, (const uint32_t*)S.signmap.p, g.ld, n, g.lay(), (const uint32_t*)ctx->bins.p, nbins, rep,
+                                      out_bytes ? (uint8_t*)S.outbytes.p : nullptr, raw_bits ? (uint8_t*)S.raw.p : nullptr, 0));
+            if (out_bytes && nb) CK(cudaMemcpyAsync(out_bytes, S.outbytes.p, (size_t)n * nb, cudaMemcpyDeviceToHost, S.stream));
+            if (raw_bits && nbins) CK(cudaMemcpyAsync(raw_bits, S.raw.p, (size_t)n * nbins, cudaMemcpyDeviceToHost, S.stream));
+            CK(cudaStreamSynchronize(S.stream));
+            return TFFT_OK;
+        }
+        // jitter, rows beyond the map, mirrored bins: the full column pass over the row-pass output, spectra from here on
+        FwdOpts fo;
+        fo.cols_only = true;
+        if ((rc = forward_images(ctx, L, ctx->res_spec, (double2*)S.spec2.p, nullptr, n, g, 0, nullptr, fo))) return rc;
+        ctx->res_stage = 0;
+    }
     ProfScope ps(ctx, S.stream, TFFT_K_EXTRACT, (double)n * (double)nbins * (16.0 + 4.0));
     CK(launch_extract(L, (const double2*)ctx->res_spec, n, ctx->res_lay, (const uint32_t*)ctx->bins.p, nbins, rep,
                       jitter ? (const double*)ctx->jitter.p : nullptr, alpha,
@@ -1027,7 +1102,7 @@ int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep, c
 
 int tfft_forward_spectrum(tfft_ctx* ctx, const uint8_t* img, int W, int H, int center, double* out_c64) {
     if (!out_c64) return TFFT_E_INVALID;
-    int rc = tfft_forward_batch(ctx, img, 1, W, H, center);
+    int rc = forward_batch_impl(ctx, img, 1, W, H, center, /*eager=*/true);
     if (rc) return rc;
     Slot& S = ctx->slot[0];
     const size_t full_bytes = 3 * (size_t)ctx->res_PH * ctx->res_PW * sizeof(double2);

@@ -1476,6 +1476,23 @@ cudaError_t launch_passthrough(const Launcher& L, const uint8_t* cover, uint8_t*
     return cudaSuccess;
 }
 
+// packed frame bits (MSB first, the order of bytes_from_bits / bits_from_bytes S:447-459) -> one bit per byte, the form
+// the embed kernels read; packed rows are `pstride` bytes apart
+__global__ void __launch_bounds__(256) unpack_bits(const uint8_t* __restrict__ packed, size_t pstride, uint8_t* __restrict__ bits, size_t nbits) {
+    const int img = blockIdx.y;
+    const uint8_t* src = packed + (size_t)img * pstride;
+    uint8_t* dst = bits + (size_t)img * nbits;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbits; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = (uint8_t)((src[i >> 3] >> (7 - (i & 7))) & 1u);
+}
+cudaError_t launch_unpack_bits(const Launcher& L, const uint8_t* packed, size_t pstride, uint8_t* bits, size_t nbits, int nimg) {
+    if (nimg == 0 || nbits == 0) return cudaSuccess;
+    const unsigned gx = (unsigned)std::min<size_t>((nbits + 255) / 256, 1024);
+    unpack_bits<<<dim3(gx, (unsigned)nimg), 256, 0, L.stream>>>(packed, pstride, bits, nbits);
+    TFFT_LAUNCH_CHECK(L);
+    return cudaSuccess;
+}
+
 // --------------------------------------------------------------------------------------------
 // Extract (read_bit_from_bin S:734-746 restated in full so ties behave like the reference,
 // rep3/rep7 majority S:468-474 / S:501-508, MSB-first packing S:447-454).

@@ -151,6 +151,8 @@ cudaError_t launch_embed_val(const Launcher& L, const uint32_t* bins, const uint
 // d_out2[0] = 1 when some bin is outside 0 < x < PW/2 (or invalid), d_out2[1] = largest row of the list
 cudaError_t launch_embed_bins_check(const Launcher& L, const uint32_t* bins, size_t nbits, SpecLayout lay, unsigned* d_out2);
 // stego[img] = cover[img] for every image with usable[img] < nbits (S:1009-1012)
+// frame bits packed MSB first (S:447-459), rows pstride bytes apart -> [nimg][nbits] one bit per byte
+cudaError_t launch_unpack_bits(const Launcher& L, const uint8_t* packed, size_t pstride, uint8_t* bits, size_t nbits, int nimg);
 cudaError_t launch_passthrough(const Launcher& L, const uint8_t* cover, uint8_t* stego, size_t img_bytes, int nimg, const uint64_t* usable, size_t nbits);
 bool fused_embed_supported(const Launcher& L);  // PassArgs::fused_embed is available (TMA column kernels in use)
 

@@ -46,6 +46,7 @@ def test_strerror_and_invalid_args_without_gpu():
     assert b"too large" in L.tfft_strerror(3)
     # null ctx is rejected before any CUDA call
     assert L.tfft_embed_batch(None, None, 0, 0, 0, None, None, 0, None, 0.5, 0, 0.01, 0.05, 0.45, None, None, None) == 1
+    assert L.tfft_embed_batch_packed(None, None, 0, 0, 0, None, None, 0, None, 0.5, 0, 0.01, 0.05, 0.45, None, None, None) == 1
     assert L.tfft_extract_bits(None, None, 0, 0, 0, None, 0, 3, None, 0.5, 0, None, None) == 1
     assert L.tfft_read_bits(None, None, 0, 3, None, 0.5, None, None) == 1
 

@@ -197,6 +197,57 @@ def test_two_phase_extract(ctx):
     assert np.array_equal(np.concatenate([raw3[0], raw7[0]]), g["raw_all"][: 912 + rest.size // 7 * 7])
 
 
+@pytest.mark.parametrize("W,H,center", [(600, 4096, False), (2100, 2500, True)])
+def test_two_phase_extract_4096_rows(ctx, W, H, center):
+    """tfft_forward_batch + tfft_read_bits on 4096-row planes (the literal S:1223-1268 flow): the forward call stops after
+    the row pass, the first read decides what the column pass leaves -- the read bits of the quarter plane (header and
+    payload reads then only vote) or, for jitter / rows beyond it / mirrored bins, the spectrum.  Every read against the
+    reference's read path on the same image, in every order of the three kinds of list."""
+    o = oracle()
+    PH, PW = synth.next_pow2(H), synth.next_pow2(W)
+    img = synth.gen_texture(W, H, 3 * W + H)
+    bins = synth.random_bins(PH, PW, 912 + 56 * 400, 23)
+    rng = np.random.default_rng(9)
+    far = ((rng.integers(0, 3, 3500).astype(np.uint32) << np.uint32(30))
+           | (rng.integers(2048, PH, 3500).astype(np.uint32) * np.uint32(PW) + rng.integers(0, PW, 3500).astype(np.uint32)))
+    jit = rng.uniform(-0.05, 0.05, 7000)
+    want = {"hdr": o.extract(img, bins[:912], 3, 0.5, center), "pay": o.extract(img, bins[912:], 7, 0.5, center),
+            "alpha": o.extract(img, bins[:7000], 7, 0.3, center), "far": o.extract(img, far, 7, 0.5, center)}
+    # (the oracle has no jitter argument: the jittered read is held against the one-call general path, test_jitter_hook)
+    jd, jr = ctx.extract_bits(img[None], bins[:7000], 7, 0.5, center, jitter=jit)
+    want["jit"] = (jd[0], jr[0])
+
+    def read(kind):
+        if kind == "hdr": return ctx.read_bits(bins[:912], 3, 0.5)
+        if kind == "pay": return ctx.read_bits(bins[912:], 7, 0.5)
+        if kind == "alpha": return ctx.read_bits(bins[:7000], 7, 0.3)
+        if kind == "far": return ctx.read_bits(far, 7, 0.5)
+        return ctx.read_bits(bins[:7000], 7, 0.5, jitter=jit)
+
+    for order in (("hdr", "pay", "alpha", "hdr", "far", "pay", "jit"), ("jit", "hdr", "pay"), ("far", "alpha"), ("pay", "jit", "hdr")):
+        ctx.forward_batch(np.stack([img, img]), center)
+        for kind in order:
+            dec, raw = read(kind)
+            for i in range(2):
+                assert np.array_equal(raw[i], want[kind][1]), (order, kind)
+                assert np.array_equal(dec[i], want[kind][0]), (order, kind)
+
+
+def test_packed_bits_entry_point(ctx):
+    """tfft_embed_batch_packed: frame bits eight to a byte, MSB first (S:447-459) -- the same stego bytes, capacities and
+    medians as the one-bit-per-byte call, for a bit count that is not a multiple of 8 and per-image bit strings."""
+    W, H, n, nbits = 600, 2160, 3, 50003
+    covers = np.stack([synth.gen_texture(W, H, 40 + i) for i in range(n)])
+    bins = synth.random_bins(4096, 1024, nbits, 7)
+    bits = synth.random_bits(n, nbits, 8)
+    a = ctx.embed_batch(covers, bins, bits)
+    b = ctx.embed_batch(covers, bins, np.packbits(bits, axis=1), packed=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert not np.array_equal(b[0], covers)   # (and the bits did go in)
+    want = oracle().embed(covers[2], bins, bits[2])
+    assert_pixels(b[0][2], want["stego"])
+
+
 def test_extract_frame(ctx):
     """Header (rep 3) + payload (rep 7) in one call == the two separate reads."""
     g = load_golden("g512_walk")
