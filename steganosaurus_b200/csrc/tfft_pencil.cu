@@ -67,13 +67,32 @@ __device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, doub
     a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
 }
 
+// a (1 + i tau)
+__device__ __forceinline__ double2 rot_t(double2 a, double tau) { return make_double2(fma(-tau, a.y, a.x), fma(tau, a.x, a.y)); }
+// dft4 of (a0, c1 u1, c2 u2, c3 u3) with r = c3 / c1: the scale factors of twiddled inputs w = c (1 + i tau), u = a (1 + i tau),
+// ride on the butterfly's own additions as FMAs -- 22 instructions for three twiddles and the butterfly instead of 28
+template <int S>
+__device__ __forceinline__ void dft4_tw(double2& a0, double2& a1, double2& a2, double2& a3, double c1, double2 u1, double c2, double2 u2,
+                                        double r, double2 u3) {
+    const double2 t0 = make_double2(fma(c2, u2.x, a0.x), fma(c2, u2.y, a0.y));
+    const double2 t1 = make_double2(fma(-c2, u2.x, a0.x), fma(-c2, u2.y, a0.y));
+    const double2 p = make_double2(fma(r, u3.x, u1.x), fma(r, u3.y, u1.y));
+    const double2 q = mul_si<S>(make_double2(fma(-r, u3.x, u1.x), fma(-r, u3.y, u1.y)));
+    a0 = make_double2(fma(c1, p.x, t0.x), fma(c1, p.y, t0.y));
+    a2 = make_double2(fma(-c1, p.x, t0.x), fma(-c1, p.y, t0.y));
+    a1 = make_double2(fma(c1, q.x, t1.x), fma(c1, q.y, t1.y));
+    a3 = make_double2(fma(-c1, q.x, t1.x), fma(-c1, q.y, t1.y));
+}
+
 // In-register DFT of R points with w = exp(S*2*pi*i/R).  Output X[k] is left at x[oidx<R>(k)].
 template <int R>
 __device__ __host__ constexpr int oidx(int k) {
     return R == 16 ? 4 * (k & 3) + (k >> 2) : R == 8 ? 2 * (k & 3) + (k >> 2) : k;
 }
 
-template <int S, int R>
+// PLAIN (R = 16): the textbook second layer instead of the folded one -- same results within rounding; the column-resident
+// embed kernel keeps it (the folded form costs it a spilled register and 6 % of its time, profiles/r2_experiments.txt)
+template <int S, int R, bool PLAIN = false>
 __device__ __forceinline__ void dft(double2* x) {
 #ifdef TFFT_EXP_NO_FP64  // timing experiment only (results are garbage): data movement and barriers without the butterflies
     return;
@@ -100,7 +119,12 @@ __device__ __forceinline__ void dft(double2* x) {
         // n = 4 n1 + n2, k = k1 + 4 k2
 #pragma unroll
         for (int n2 = 0; n2 < 4; n2++) dft4<S>(x[n2], x[4 + n2], x[8 + n2], x[12 + n2]);  // y[n2][k1] at x[4 k1 + n2]
-        // twiddle w16^{n2 k1}
+#ifdef TFFT_DFT16_PLAIN
+        constexpr bool plain = true;
+#else
+        constexpr bool plain = PLAIN;
+#endif
+        if constexpr (plain) {  // the textbook form: nine constant twiddles w16^{n2 k1}, then four plain 4-point butterflies
         x[5] = cmulc<S>(x[5], C16, S16);    // 1
         x[6] = cmulc<S>(x[6], C8, C8);      // 2
         x[7] = cmulc<S>(x[7], S16, C16);    // 3
@@ -112,6 +136,15 @@ __device__ __forceinline__ void dft(double2* x) {
         x[15] = cmulc<S>(x[15], -C16, -S16);  // 9
 #pragma unroll
         for (int k1 = 0; k1 < 4; k1++) dft4<S>(x[4 * k1], x[4 * k1 + 1], x[4 * k1 + 2], x[4 * k1 + 3]);
+        } else {
+        // the constant twiddles w16^{n2 k1} = c (1 + i tau) folded into the second layer (dft4_tw): 16 instructions fewer
+        constexpr double T1 = 0.41421356237309504880;  // tan(pi/8) = S16 / C16
+        constexpr double T3 = 2.41421356237309504880;  // cot(pi/8) = C16 / S16
+        dft4<S>(x[0], x[1], x[2], x[3]);
+        dft4_tw<S>(x[4], x[5], x[6], x[7], C16, rot_t(x[5], S * T1), C8, rot_t(x[6], S * 1.0), T1, rot_t(x[7], S * T3));            // w^1, w^2, w^3
+        dft4_tw<S>(x[8], x[9], x[10], x[11], C8, rot_t(x[9], S * 1.0), 1.0, mul_si<S>(x[10]), -1.0, rot_t(x[11], -S * 1.0));         // w^2, w^4, w^6
+        dft4_tw<S>(x[12], x[13], x[14], x[15], S16, rot_t(x[13], S * T3), -C8, rot_t(x[14], -S * 1.0), -T3, rot_t(x[15], S * T1));   // w^3, w^6, w^9
+        }
     }
 }
 
@@ -228,7 +261,8 @@ __device__ __forceinline__ double u8_to_double(unsigned v) {
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
 // TW_SHIFT: tw[m << TW_SHIFT] = w_N^m (the global table holds w_16384^k; a shared-memory copy of w_N^m, m < 256, has shift 0)
 // TW_READY: the table already holds the twiddles of this direction (conjugated for the inverse)
-template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256, int TW_SHIFT = TW_LOG2 - LOG2N, bool TW_READY = false>
+template <int S, int LOG2N, int VEC, bool FROM_U8, int NZ = (1 << LOG2N) / 256, int TW_SHIFT = TW_LOG2 - LOG2N, bool TW_READY = false,
+          bool PLAIN = false>
 __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2* __restrict__ tw,
                                        const uint8_t* urow, int W, int ch, int negmask /*center: parity of y, or -1*/) {
     using G = Geo<LOG2N, VEC>;
@@ -250,7 +284,7 @@ __device__ __forceinline__ void stage1(double2* L, int tt, int c, const double2*
                 x[n] = n < NZ ? L[(n * 256 + m) * VEC + c] : make_double2(0.0, 0.0);
             }
         }
-        dft<S, G::R1>(x);
+        dft<S, G::R1, PLAIN>(x);
         double2 w1 = tw[(size_t)m << TW_SHIFT];
         if (S < 0 && !TW_READY) w1.y = -w1.y;
         twiddle<G::R1>(x, w1);
@@ -798,6 +832,9 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
     using G = Geo<LOG2N, VEC>;
     constexpr int BOX_ROWS = 256, NBOX = G::N / BOX_ROWS;
     static_assert(NZ >= 1 && NZ <= NBOX && K3N >= 1 && K3N <= 16, "block counts");
+    // its six radix-16 butterflies keep the textbook second layer: folding the forward three costs a spilled register
+    // (+6 % kernel time), folding the inverse three changes nothing (profiles/r2_experiments.txt)
+    constexpr bool FWD_PLAIN = true, INV_PLAIN = true;
     constexpr bool EARLY_PREFETCH = NZ <= 9;  // the landing area stays clear of the inverse exchange image
     // Results leave through the warp slices of X, eight row blocks (64 KB) at a time.  One or two extra blocks (UHD: the
     // ninth) are staged behind them in the 16 KB X has left, so both box stores of a pair are issued together; more than
@@ -860,7 +897,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
         }
         // ================= forward column transform (as pencil_col_tma_w<+1, NZ, 16>) =================
         mbar_wait(&full_bar, parity);
-        stage1<+1, LOG2N, VEC, false, NZ, 0>(L, tt, c, tw_s, nullptr, 0, 0, -1);
+        stage1<+1, LOG2N, VEC, false, NZ, 0, false, FWD_PLAIN>(L, tt, c, tw_s, nullptr, 0, 0, -1);
         cp_async_wait_all();
         __syncthreads();
         double2 x[16];
@@ -875,7 +912,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
             fence_async_proxy();
             issue_load(nplane, ng);
         }
-        dft<+1, 16>(x);
+        dft<+1, 16, FWD_PLAIN>(x);
         twiddle<16>(x, tw_s[16 * m]);  // w_256^m
         double2 z[16];
         mbar_wait(&xfree_a, parity);
@@ -890,7 +927,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
         __syncwarp();
 #pragma unroll
         for (int n = 0; n < 16; n++) z[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
-        dft<+1, 16>(z);  // z[oidx(k3)] = F[row k1 + 16 m + 256 k3][column 2 g + c]
+        dft<+1, 16, FWD_PLAIN>(z);  // z[oidx(k3)] = F[row k1 + 16 m + 256 k3][column 2 g + c]
         // ================= median inputs: q of every element (exact double, two word planes) + the sample =================
         {
             const size_t qbase = ((((size_t)plane * gpp + g) * 16 + k1) * 128 + (tid & 31)) * 4;  // in words
@@ -948,7 +985,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
         {
 #pragma unroll
             for (int n = 0; n < 16; n++) x[n] = z[oidx<16>(n)];
-            dft<-1, 16>(x);
+            dft<-1, 16, INV_PLAIN>(x);
             double2 w1 = tw_s[mp];
             w1.y = -w1.y;
             twiddle<16>(x, w1);  // x[oidx(k)] = exchange-1 entry k * 256 + mp
@@ -965,7 +1002,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
             issue_load(nplane, ng);
         }
         // stage 2, warp-local transpose, stage 3 (as pencil_col_tma_w<-1>)
-        dft<-1, 16>(z);
+        dft<-1, 16, INV_PLAIN>(z);
         {
             double2 w2 = tw_s[16 * m];
             w2.y = -w2.y;
@@ -982,7 +1019,7 @@ __global__ void __launch_bounds__(512, 1) pencil_col_embed_w(const __grid_consta
         __syncwarp();
 #pragma unroll
         for (int n = 0; n < 16; n++) x[n].y = Xw[((m << 4) | (n ^ m)) * VEC + c];
-        dft<-1, 16>(x);  // x[oidx(k3)] = output row k1 + 16 m + 256 k3 of column c
+        dft<-1, 16, INV_PLAIN>(x);  // x[oidx(k3)] = output row k1 + 16 m + 256 k3 of column c
         // ---- first half of the results: rows with k3 < 8 (and, ONE_ROUND, the one or two blocks behind them)
         __syncwarp();
 #pragma unroll
