@@ -257,6 +257,13 @@ __device__ __forceinline__ double u8_to_double(unsigned v) {
 #endif
 }
 
+// exact u8 -> double of HALF the value: 2^51 + v/2 has v in its low mantissa word.  The forward half-spectrum row kernel
+// feeds its transform with halved pixels, so the Hermitian split's factors 1/2 are already in (a power of two commutes
+// with every rounding on the way: bit-identical results, 32 multiplications fewer per thread and plane)
+__device__ __forceinline__ double u8_to_half_double(unsigned v) {
+    return __hiloint2double(0x43200000, (int)v) - 2251799813685248.0;
+}
+
 // ---- stage 1: radix R1, stride 256, in place in L (or from the u8 row for M_U8_FWD) --------
 // NZ: input blocks n >= NZ (rows n*256 ..) are known to be zero: not read, and their butterflies fold away
 // TW_SHIFT: tw[m << TW_SHIFT] = w_N^m (the global table holds w_16384^k; a shared-memory copy of w_N^m, m < 256, has shift 0)
@@ -1371,7 +1378,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
 #pragma unroll
                 for (int n = 0; n < G::R1; n++) {
                     const unsigned o = (unsigned)((n * 256 + j * G::TP) * (WIDE ? 6 : 3)) + (unsigned)ch;
-                    double v0 = u8_to_double(r0[o]), v1 = u8_to_double(r1[o]);
+                    double v0 = u8_to_half_double(r0[o]), v1 = u8_to_half_double(r1[o]);  // Z / 2 from here on
                     if constexpr (CENTER) {  // apply_center S:392: (-1)^(x+y); pair: x parity == m parity; wide: x = 2n, 2n+1
                         if constexpr (FOLD && !WIDE) {  // rows y0 and y0 + 4096 have the same parity
                             if ((m + y0) & 1) { v0 = -v0; v1 = -v1; }
@@ -1418,8 +1425,8 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                                                0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913};
                     const double2 z = x[oidx<16>(k3)];
                     const double2 zn = Lp[-G::TP * k3];
-                    const double2 E = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));
-                    const double2 O = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));
+                    const double2 E = make_double2(z.x + zn.x, z.y - zn.y);   // (z, zn hold Z / 2)
+                    const double2 O = make_double2(z.y + zn.y, zn.x - z.x);
                     const double2 w = k3 == 0 ? wb : cmulc<+1>(wb, C32[k3], S32[k3]);
                     const double2 t = cmul(w, O);
                     const double2 XK = make_double2(E.x + t.x, E.y + t.y);   // X[k]
@@ -1427,7 +1434,8 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     keep[k3] = unit == 0 ? XK : XM;
                     Sm[k3 * G::TP + tt] = unit == 0 ? XM : XK;
                 }
-                if (tt == 0) Sm[8 * G::TP] = x[oidx<16>(8)];                  // X[N/2] = Z[N/2]
+                const double2 xnh = make_double2(2.0 * x[oidx<16>(8)].x, 2.0 * x[oidx<16>(8)].y);  // X[N/2] = Z[N/2]
+                if (tt == 0) Sm[8 * G::TP] = xnh;
                 __syncthreads();
                 const size_t yA = (size_t)(y0 & (FR - 1));
                 double2* rowA = a.spec + (((size_t)img * 3 + ch) * a.PH + yA) * a.ld;
@@ -1441,7 +1449,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     rowB[col0 + cstep * k3] = cmul(csub(X0, X1), wy);
                 }
                 if (unit == 0 && tt == 0) {
-                    const double2 X0 = x[oidx<16>(8)], X1 = So[8 * G::TP];
+                    const double2 X0 = xnh, X1 = So[8 * G::TP];
                     rowA[NH] = cadd(X0, X1);
                     rowB[NH] = cmul(csub(X0, X1), wy);
                 }
@@ -1464,14 +1472,14 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                                                0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613, 0.98078528040323044913};
                     const double2 z = x[oidx<16>(k3)];
                     const double2 zn = Lp[-G::TP * k3];
-                    const double2 E = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));
-                    const double2 O = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));
+                    const double2 E = make_double2(z.x + zn.x, z.y - zn.y);   // (z, zn hold Z / 2)
+                    const double2 O = make_double2(z.y + zn.y, zn.x - z.x);
                     const double2 w = k3 == 0 ? wb : cmulc<+1>(wb, C32[k3], S32[k3]);
                     const double2 t = cmul(w, O);
                     out0[tt + G::TP * k3] = make_double2(E.x + t.x, E.y + t.y);       // X[k]
                     outm[-G::TP * k3] = make_double2(E.x - t.x, t.y - E.y);           // X[N-k] = conj(E - t)
                 }
-                if (tt == 0) out0[NH] = x[oidx<16>(8)];                               // X[N/2] = Z[N/2]
+                if (tt == 0) out0[NH] = make_double2(2.0 * x[oidx<16>(8)].x, 2.0 * x[oidx<16>(8)].y);  // X[N/2] = Z[N/2]
                 if (tt >= 1 && tt < 16) out0[N + tt] = make_double2(0.0, 0.0);        // pad columns N+1 .. N+15
             } else {
 #pragma unroll
@@ -1479,8 +1487,8 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     const int k = tt + G::TP * k3;
                     const double2 z = x[oidx<16>(k3)];
                     const double2 zn = Lp[-G::TP * k3];  // Z[N-k] = L[(N-k) - N/2]; k = 0 reads L[NH] = Z[0]
-                    const double2 F0 = make_double2(0.5 * (z.x + zn.x), 0.5 * (z.y - zn.y));   // (Z[k] + conj Z[N-k]) / 2
-                    const double2 F1 = make_double2(0.5 * (z.y + zn.y), 0.5 * (zn.x - z.x));   // (Z[k] - conj Z[N-k]) / 2i
+                    const double2 F0 = make_double2(z.x + zn.x, z.y - zn.y);   // (Z[k] + conj Z[N-k]) / 2  (z, zn hold Z / 2)
+                    const double2 F1 = make_double2(z.y + zn.y, zn.x - z.x);   // (Z[k] - conj Z[N-k]) / 2i
                     if constexpr (FOLD) {  // rows y0 and y0 + 4096 of the plane: A and B (an absent second row is zero)
                         out0[k] = nrows == 2 ? cadd(F0, F1) : F0;
                         out1[k] = cmul(nrows == 2 ? csub(F0, F1) : F0, wy);
@@ -1490,7 +1498,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
                     }
                 }
                 if (tt < 16) {  // Nyquist column (real) and the zero pad columns N/2+1 .. N/2+15
-                    const double2 z8 = x[oidx<16>(8)];
+                    const double2 z8 = make_double2(2.0 * x[oidx<16>(8)].x, 2.0 * x[oidx<16>(8)].y);  // Z[N/2]
                     if constexpr (FOLD) {
                         const double f1 = nrows == 2 ? z8.y : 0.0;
                         out0[NH + tt] = tt == 0 ? make_double2(z8.x + f1, 0.0) : make_double2(0.0, 0.0);

@@ -49,10 +49,12 @@ def test_fused_embed_vs_oracle_and_unfused(ctx, W, H, nbits, center):
     assert_pixels(stego[0], want["stego"])
     with unfused_context() as c2:
         s2, u2, m2 = c2.embed_batch(cover[None], bins, bits, 0.5, center)
-    assert_pixels(stego[0], s2[0])  # same butterflies; |F| at the bins by sqrt(re^2 + im^2) here, hypot() there (<= 1 ulp apart)
+    # the same transform up to rounding (the fused kernel keeps the textbook radix-16 butterfly, the others fold its constant
+    # twiddles into FMAs); |F| at the bins by sqrt(re^2 + im^2) here, hypot() there
+    assert_pixels(stego[0], s2[0])
     assert (stego != s2).mean() < 1e-6
     assert np.array_equal(usable, u2)
-    assert np.abs(med - m2).max() <= 1e-15 * np.abs(m2).max()  # sqrt(q) vs hypot() of the selected element
+    assert np.abs(med - m2).max() <= 1e-13 * np.abs(m2).max()
     _, raw = ctx.extract_bits(stego, bins, 1, 0.5, center)
     _, wraw = o.extract(want["stego"], bins, 1, 0.5, center)
     assert np.array_equal(raw[0], wraw)

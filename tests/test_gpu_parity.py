@@ -314,7 +314,9 @@ def test_median_exact_many_planes(ctx):
         for p in range(3):
             mags = np.hypot(F[p].real, F[p].imag).ravel()
             want = np.partition(mags, mags.size // 2)[mags.size // 2]
-            assert abs(med[i, p] - want) <= 1e-15 * want, (i, p, med[i, p], want)  # (4096-row planes: sqrt of the q order statistic)
+            # (4096-row planes: sqrt of the q order statistic, taken inside the column-resident pass, whose butterflies round
+            # differently in the last bit from the pass behind the spectrum hook: 1e-13, against 1e-11 for the oracle's medians)
+            assert abs(med[i, p] - want) <= 1e-13 * want, (i, p, med[i, p], want)
 
 
 @pytest.mark.parametrize("W,H,n", [(700, 3000, 3), (4096, 4096, 1), (3840, 2160, 2), (512, 2100, 4)])
@@ -330,7 +332,9 @@ def test_median_4096_rows(ctx, W, H, n):
         for p in range(3):
             mags = np.hypot(F[p].real, F[p].imag).ravel()
             want = np.partition(mags, mags.size // 2)[mags.size // 2]
-            assert abs(med[i, p] - want) <= 1e-15 * want, (i, p, med[i, p], want)  # (4096-row planes: sqrt of the q order statistic)
+            # (4096-row planes: sqrt of the q order statistic, taken inside the column-resident pass, whose butterflies round
+            # differently in the last bit from the pass behind the spectrum hook: 1e-13, against 1e-11 for the oracle's medians)
+            assert abs(med[i, p] - want) <= 1e-13 * want, (i, p, med[i, p], want)
         if i == 0:
             Fo = o.forward_spectrum(imgs[i])
             wus = sum(o.count_plane(Fo[p], 0.05, 0.45, 0.01 * o.median_abs(Fo[p])) for p in range(3))

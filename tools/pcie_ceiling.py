@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--perm", default="identity", choices=["identity", "interleave"])
     ap.add_argument("--gib", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=6)
+    ap.add_argument("--wc", action="store_true", help="host buffers from tfft_host_alloc_wc (write-combined pinned memory)")
     a = ap.parse_args()
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     ndev = torch.cuda.device_count()
@@ -31,7 +32,21 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = int(a.gib * (1 << 30))
-    h_up, h_up2, h_dn = (torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(3))
+    if a.wc:
+        import ctypes
+        import sys
+        import numpy as np
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from steganosaurus_b200 import _lib
+        L = _lib.load()
+
+        def wc_tensor():
+            p = L.tfft_host_alloc_wc(n)
+            assert p, "tfft_host_alloc_wc failed"
+            return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(p)))
+        h_up, h_up2, h_dn = wc_tensor(), wc_tensor(), wc_tensor()
+    else:
+        h_up, h_up2, h_dn = (torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(3))
     d_up, d_up2, d_dn = (torch.empty(n, dtype=torch.uint8, device=dev) for _ in range(3))
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
     flag = torch.zeros(1, device=dev)
@@ -76,7 +91,7 @@ def main():
     t_up, t_dn, t_both, t_mix = timed(up), timed(down), timed(both), timed(mix)
     gb = n / 1e9
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "perm": a.perm, "devices": perm[:world], "chunk_GiB": a.gib,
+        print(json.dumps({"n_gpus": world, "perm": a.perm, "write_combined": bool(a.wc), "devices": perm[:world], "chunk_GiB": a.gib,
                           "h2d_GBps_total": round(world * gb / t_up, 1), "d2h_GBps_total": round(world * gb / t_dn, 1),
                           "both_GBps_total": round(world * 2 * gb / t_both, 1), "mix_2up_1down_GBps_total": round(world * 3 * gb / t_mix, 1),
                           "per_gpu": {"h2d": round(gb / t_up, 1), "d2h": round(gb / t_dn, 1), "both_each_way": round(gb / t_both, 1),
