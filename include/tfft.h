@@ -82,10 +82,6 @@ int tfft_set_workspace_limit(tfft_ctx* ctx, size_t bytes);
 int tfft_set_adaptive_alpha(tfft_ctx* ctx, int on);
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* tfft_host_alloc(size_t bytes);
-/* The same, write-combined (cudaHostAllocWriteCombined): for buffers the CPU only WRITES (covers, frame bits on their way
- * up) or never touches (a stego buffer that one call fills from the device and the next uploads); CPU reads of such
- * memory are very slow.  Released with tfft_host_free as well. */
-void* tfft_host_alloc_wc(size_t bytes);
 void tfft_host_free(void* p);
 /* Number of kernels this library has launched through ctx since creation. */
 uint64_t tfft_launch_count(const tfft_ctx* ctx);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("TFFT_LIB") or os.path.join(PKG, "libtfft_b200.so")  #
 # every symbol include/tfft.h declares
 SYMBOLS = [
     "tfft_create", "tfft_destroy", "tfft_abi_version", "tfft_strerror", "tfft_last_cuda_error",
-    "tfft_set_workspace_limit", "tfft_set_adaptive_alpha", "tfft_host_alloc", "tfft_host_alloc_wc", "tfft_host_free", "tfft_launch_count",
+    "tfft_set_workspace_limit", "tfft_set_adaptive_alpha", "tfft_host_alloc", "tfft_host_free", "tfft_launch_count",
     "tfft_embed_batch", "tfft_embed_batch_packed", "tfft_embed_batch_dev", "tfft_extract_bits", "tfft_extract_bits_dev",
     "tfft_forward_batch", "tfft_read_bits", "tfft_forward_spectrum", "tfft_fft2d", "tfft_fft2d_dev",
     "tfft_fft_pass_dev", "tfft_median_capacity_dev", "tfft_extract_frame", "tfft_extract_frame_dev",
@@ -55,8 +55,6 @@ def load() -> C.CDLL:
     L.tfft_set_adaptive_alpha.restype = i
     L.tfft_host_alloc.argtypes = [sz]
     L.tfft_host_alloc.restype = vp
-    L.tfft_host_alloc_wc.argtypes = [sz]
-    L.tfft_host_alloc_wc.restype = vp
     L.tfft_host_free.argtypes = [vp]
     L.tfft_host_free.restype = None
     L.tfft_launch_count.argtypes = [vp]

@@ -661,11 +661,6 @@ void* tfft_host_alloc(size_t bytes) {
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
-void* tfft_host_alloc_wc(size_t bytes) {
-    void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return p;
-}
 void tfft_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int tfft_create(int device, tfft_ctx** out) {
