@@ -4,12 +4,16 @@
 // --key / --wrap-pass (a raw or passphrase-wrapped 32-byte master key, S:576-662, S:1020-1040) are supported;
 // not carried over (out of scope): gen-key and the experimental --adaptive_alpha /
 // --cover_dependent_path (upstream documents both as broken).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../../../include/tfft.h"
 #include "../../../include/tfft_host.h"
@@ -72,12 +76,42 @@ bool parse(int argc, char** argv, Args& A) {
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-tfft_ctx* open_ctx() {
+// TFFT_CLI_TIMING=1: wall milliseconds of the phases of one invocation on stderr
+struct Phases {
+    bool on = getenv("TFFT_CLI_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[timing] %-28s %8.1f ms  (at %8.1f ms)\n", what, std::chrono::duration<double, std::milli>(now - last).count(),
+                std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
+// A one-shot process pays for the CUDA start-up (driver initialisation, context, module) on every call; it is the largest
+// part of a small image's wall time.  So the context is opened on a second thread the moment the arguments are parsed,
+// under the PNG decode, the KDF and the walk; on a multi-GPU node only the GPU that will be used is made visible (the
+// driver otherwise initialises all of them); and the process leaves through _Exit once its output is flushed instead
+// of tearing the context down.
+std::future<tfft_ctx*> open_ctx_async() {
     const char* d = getenv("TFFT_DEVICE");
-    tfft_ctx* c = nullptr;
-    const int rc = tfft_create(d ? atoi(d) : 0, &c);
-    if (rc) { fprintf(stderr, "turtlefft: cannot open the GPU context: %s\n", tfft_strerror(rc)); exit(1); }
-    return c;
+    int dev = d ? atoi(d) : 0;
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {  // (the environment is settled before the second thread exists)
+        setenv("CUDA_VISIBLE_DEVICES", std::to_string(dev).c_str(), 1);
+        dev = 0;
+    }
+    return std::async(std::launch::async, [dev] {
+        tfft_ctx* c = nullptr;
+        const int rc = tfft_create(dev, &c);
+        if (rc) { fprintf(stderr, "turtlefft: cannot open the GPU context: %s\n", tfft_strerror(rc)); exit(1); }
+        return c;
+    });
+}
+[[noreturn]] void leave(int code) {
+    fflush(stdout);
+    fflush(stderr);
+    _Exit(code);
 }
 [[noreturn]] void die_tfft(tfft_ctx* c, int rc) {
     fprintf(stderr, "turtlefft: %s (%s)\n", tfft_strerror(rc), tfft_last_cuda_error(c));
@@ -108,6 +142,8 @@ bool load_key(const Args& A, uint8_t master[32]) {
 }
 
 void do_embed(const Args& A) {
+    Phases ph;
+    auto ctx_f = open_ctx_async();
     int W, H;
     uint8_t* img = tfft_host_png_load(A.in.c_str(), &W, &H);
     if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:910
@@ -131,7 +167,9 @@ void do_embed(const Args& A) {
     const int wrc = tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, nbits, bins.data(), nullptr, nullptr, 0);
     std::vector<double> jit;
     if (A.jitter != 0.0 && wrc == 0) { jit.resize(nbits); tfft_host_jitter(sub, bins.data(), nbits, A.jitter, jit.data()); }
-    tfft_ctx* ctx = open_ctx();
+    ph.mark("png + kdf + frame + walk");
+    tfft_ctx* ctx = ctx_f.get();
+    ph.mark("wait for the gpu context");
     std::vector<uint8_t> out((size_t)W * H * 3);
     uint64_t usable = 0;
     double med[3];
@@ -144,14 +182,17 @@ void do_embed(const Args& A) {
         exit(1);
     }
     if (rc) die_tfft(ctx, rc);
+    ph.mark("tfft_embed_batch");
     if (!tfft_host_png_save(A.out.c_str(), out.data(), W, H)) { fprintf(stderr, "PNG write failed: %s\n", A.out.c_str()); exit(1); }  // S:1105
     fprintf(stdout, "Embedded %zu bits into %s (payload %u bytes, ver=2, salt/nonce in header)\n", nbits, A.out.c_str(),
             (unsigned)A.secret.size());  // S:1107
-    tfft_hostlib_free(img);
-    tfft_destroy(ctx);
+    ph.mark("png encode");
+    leave(0);
 }
 
 void do_extract(const Args& A) {
+    Phases ph;
+    auto ctx_f = open_ctx_async();
     int W, H;
     uint8_t* img = tfft_host_png_load(A.in.c_str(), &W, &H);
     if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:1115
@@ -160,13 +201,15 @@ void do_extract(const Args& A) {
     const bool raw_key = load_key(A, master);
     if (raw_key) tfft_host_turtle_keys(master, 32, path_key, sub);
     else tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
-    tfft_ctx* ctx = open_ctx();
-    int rc = tfft_forward_batch(ctx, img, 1, W, H, A.center ? 1 : 0);
-    if (rc) die_tfft(ctx, rc);
     std::vector<uint32_t> bins(912);
     if (tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, 912, bins.data(), nullptr, nullptr, 0)) {
         fprintf(stderr, "Magic not found.\n"); exit(1);  // not even room for a header
     }
+    ph.mark("png + keys + header walk");
+    tfft_ctx* ctx = ctx_f.get();
+    ph.mark("wait for the gpu context");
+    int rc = tfft_forward_batch(ctx, img, 1, W, H, A.center ? 1 : 0);
+    if (rc) die_tfft(ctx, rc);
     std::vector<double> jit;
     if (A.jitter != 0.0) { jit.resize(912); tfft_host_jitter(sub, bins.data(), 912, A.jitter, jit.data()); }
     uint8_t hdr[38];
@@ -188,6 +231,7 @@ void do_extract(const Args& A) {
     std::vector<uint8_t> rest((size_t)clen + 16);
     if ((rc = tfft_read_bits(ctx, bins.data() + 912, nb - 912, 7, jit.empty() ? nullptr : jit.data() + 912, A.alpha, rest.data(), nullptr)))
         die_tfft(ctx, rc);
+    ph.mark("forward + header + payload");
     const int opened = raw_key ? tfft_host_open_payload_key(master, hdr, rest.data(), clen)
                                : tfft_host_open_payload((const uint8_t*)A.pass.data(), A.pass.size(), A.iters, hdr, rest.data(), clen);
     memset(master, 0, sizeof(master));
@@ -196,8 +240,8 @@ void do_extract(const Args& A) {
     }
     std::string secret((const char*)rest.data(), clen);
     printf("%s\n", secret.c_str());  // S:1311
-    tfft_hostlib_free(img);
-    tfft_destroy(ctx);
+    ph.mark("open payload (kdf + aead)");
+    leave(0);
 }
 
 }  // namespace
