@@ -101,18 +101,36 @@ class ImagePipeline:
         assert len(covers) == len(outs) == len(secrets)
         P = params
         res = [Result(path=o) for o in outs]
-        imgs: List[Optional[np.ndarray]] = list(self.pool.map(_load_or_none, covers))
-        for r, im, c in zip(res, imgs, covers):
-            if im is None:
+        # Chunks are planned from the PNG headers alone; decode and KDF + AEAD + Rep-3/Rep-7 framing (600 000 PBKDF2
+        # iterations each by default) are queued on the pool chunk by chunk, and the GPU call of a chunk only waits for
+        # ITS images -- the pool decodes / frames the later chunks and encodes the earlier ones meanwhile.
+        shapes = list(self.pool.map(_png_shape_or_none, covers))
+        for r, sh, c in zip(res, shapes, covers):
+            if sh is None:
                 r.error = f"Failed to load {c}"
-        live = [i for i, im in enumerate(imgs) if im is not None]
+        live = [i for i, sh in enumerate(shapes) if sh is not None]
         salts_ = [os.urandom(16) if salts is None else salts[i] for i in range(len(covers))]
-        # KDF + AEAD + Rep-3/Rep-7 framing per image on the pool (600 000 PBKDF2 iterations each by default)
-        frames = dict(zip(live, self.pool.map(lambda i: host.frame_bits(pw, salts_[i], P.pbkdf2_iter, secrets[i])[0], live)))
-        plan = plan_embed_groups([imgs[i].shape[:2] for i in live], [len(secrets[i]) for i in live], self.chunk)
+        plan = plan_embed_groups([shapes[i] for i in live], [len(secrets[i]) for i in live], self.chunk)
+        load_f, frame_f = {}, {}
+        for grp in plan:
+            for k in grp:
+                i = live[k]
+                load_f[i] = self.pool.submit(_load_or_none, covers[i])
+                frame_f[i] = self.pool.submit(lambda i=i: host.frame_bits(pw, salts_[i], P.pbkdf2_iter, secrets[i])[0])
         saves = []
         for grp in plan:
-            idx = [live[k] for k in grp]
+            idx = []
+            imgs, frames = {}, {}
+            for k in grp:
+                i = live[k]
+                im = load_f.pop(i).result()
+                fr = frame_f.pop(i).result()
+                if im is None or im.shape[:2] != tuple(shapes[i]):   # (the header parsed, the image data did not decode)
+                    res[i].error = f"Failed to load {covers[i]}"
+                    continue
+                idx.append(i); imgs[i] = im; frames[i] = fr
+            if not idx:
+                continue
             H, W, _ = imgs[idx[0]].shape
             nbits = frames[idx[0]].size
             try:
@@ -153,14 +171,26 @@ class ImagePipeline:
     def extract_files(self, stegos: Sequence[str], pw: bytes, params: Params = Params()) -> List[Result]:
         P = params
         res = [Result(path=s) for s in stegos]
-        imgs = list(self.pool.map(_load_or_none, stegos))
-        for r, im, s in zip(res, imgs, stegos):
-            if im is None:
+        shapes = list(self.pool.map(_png_shape_or_none, stegos))   # (headers only: the chunks are planned before anything is decoded)
+        for r, sh, s in zip(res, shapes, stegos):
+            if sh is None:
                 r.error = f"Failed to load {s}"
-        live = [i for i, im in enumerate(imgs) if im is not None]
+        live = [i for i, sh in enumerate(shapes) if sh is not None]
+        plan = plan_extract_groups([shapes[i] for i in live], self.chunk)
+        load_f = {live[k]: self.pool.submit(_load_or_none, stegos[live[k]]) for grp in plan for k in grp}   # queued in chunk order
         opens = []
-        for grp in plan_extract_groups([imgs[i].shape[:2] for i in live], self.chunk):
-            idx = [live[k] for k in grp]
+        for grp in plan:
+            idx = []
+            imgs = {}
+            for k in grp:
+                i = live[k]
+                im = load_f.pop(i).result()
+                if im is None or im.shape[:2] != tuple(shapes[i]):
+                    res[i].error = f"Failed to load {stegos[i]}"
+                    continue
+                idx.append(i); imgs[i] = im
+            if not idx:
+                continue
             H, W, _ = imgs[idx[0]].shape
             PH, PW = next_pow2(H), next_pow2(W)
             self.ctx.forward_batch(np.stack([imgs[i] for i in idx]), P.center)   # one forward FFT per image, kept resident
@@ -210,6 +240,21 @@ class ImagePipeline:
             else:
                 res[i].error = "Auth failed (wrong pass or data corrupted)."
         return res
+
+
+def _png_shape_or_none(path: str):
+    """(H, W) from the IHDR chunk of a PNG file (the first 24 bytes), None when it is not one."""
+    try:
+        with open(path, "rb") as f:
+            h = f.read(24)
+    except OSError:
+        return None
+    if len(h) < 24 or h[:8] != b"\x89PNG\r\n\x1a\n" or h[12:16] != b"IHDR":
+        return None
+    W, H = int.from_bytes(h[16:20], "big"), int.from_bytes(h[20:24], "big")
+    if W <= 0 or H <= 0 or W > 16384 or H > 16384:   # TFFT_MAX_DIM: the loader refuses these as well
+        return None
+    return (H, W)
 
 
 def _load_or_none(path: str):

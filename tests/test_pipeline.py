@@ -35,10 +35,16 @@ def test_embed_files_png_pool_roundtrip_with_stub_context(tmp_path):
         host.png_save(p, synth.gen_texture(w, h, i))
         covers.append(p); outs.append(str(tmp_path / f"o{i}.png")); secrets.append(b"x" * (3 + i))
     covers.append(str(tmp_path / "missing.png")); outs.append(str(tmp_path / "o3.png")); secrets.append(b"zz")
+    # a file whose header says 256x192 (it is planned into the first chunk) but whose image data is cut off
+    trunc = str(tmp_path / "trunc.png")
+    open(trunc, "wb").write(open(covers[0], "rb").read()[:200])
+    covers.append(trunc); outs.append(str(tmp_path / "o4.png")); secrets.append(b"xxx")
+    assert pipeline._png_shape_or_none(covers[0]) == (192, 256) and pipeline._png_shape_or_none(trunc) == (192, 256)
+    assert pipeline._png_shape_or_none(covers[3]) is None and pipeline._png_shape_or_none(__file__) is None
     with pipeline.ImagePipeline(_StubCtx(), workers=3, chunk=2) as pl:
         res = pl.embed_files(covers, outs, secrets, PASS, pipeline.Params(pbkdf2_iter=10))
-    assert [r.ok for r in res] == [True, True, True, False]
-    assert res[3].error.startswith("Failed to load")
+    assert [r.ok for r in res] == [True, True, True, False, False]
+    assert res[3].error.startswith("Failed to load") and res[4].error.startswith("Failed to load")
     assert [r.nbits for r in res[:3]] == [912 + 56 * (3 + i + 16) for i in range(3)]
     for c, o in zip(covers[:3], outs[:3]):
         assert np.array_equal(host.png_load(c), host.png_load(o))
