@@ -707,7 +707,7 @@ def run_ours(args):
     ach = (nbytes / 1e9) / (ms / 1e3) if ms > 0 else 0.0
     kernels = {k: {"groups": v[0], "ms": round(v[1], 3), "GBps": round((v[2] / 1e9) / (v[1] / 1e3), 1) if v[1] > 0 else None}
                for k, v in prof.items() if v[0]}
-    traffic = None
+    traffic, other_pipes = None, None
     tpath = os.path.join(ROOT, "profiles", "dominant_traffic.json")
     if os.path.exists(tpath):
         try:
@@ -715,6 +715,7 @@ def run_ours(args):
             if tj and groups:
                 # ncu-measured DRAM bytes per image x images in one launch group of this run
                 traffic = tj["dram_bytes_per_image"] * (nbytes / groups) / tj["algorithmic_bytes_per_image"]
+                other_pipes = tj.get("other_pipes")  # what else the capture says is busy (the kernel is FP64 work)
         except Exception:
             pass
     mp_per_step = B * W * H / 1e6   # per rank; every rank runs the same batch size (weak scaling)
@@ -738,7 +739,8 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                      "frac": ach / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "launch_groups": groups, "avg_ms_per_group": ms / groups if groups else None,
-                     "algorithmic_bytes_per_group": nbytes / groups if groups else None, "kernels": kernels},
+                     "algorithmic_bytes_per_group": nbytes / groups if groups else None, "other_pipes_ncu": other_pipes,
+                     "kernels": kernels},
         "cpu_baseline": cpu_base,
     }
     print(json.dumps(line), flush=True)

@@ -20,6 +20,15 @@
 
 namespace {
 
+// Every way out of the process after the GPU context thread has been started: flush and _Exit.  exit() would run the
+// CUDA runtime's teardown under that thread (a "cannot open the GPU context" line after the real error message), and
+// tearing a context down is time a one-shot process does not need to spend.
+[[noreturn]] void leave(int code) {
+    fflush(stdout);
+    fflush(stderr);
+    _Exit(code);
+}
+
 struct Args {
     std::string mode, in, out, secret, pass, key, wrap_pass;
     double alpha = 0.50, rmin = 0.05, rmax = 0.45, magmin = 0.01, density = 0.7, jitter = 0.0;  // S:375-381
@@ -104,18 +113,14 @@ std::future<tfft_ctx*> open_ctx_async() {
     return std::async(std::launch::async, [dev] {
         tfft_ctx* c = nullptr;
         const int rc = tfft_create(dev, &c);
-        if (rc) { fprintf(stderr, "turtlefft: cannot open the GPU context: %s\n", tfft_strerror(rc)); exit(1); }
+        if (rc) { fprintf(stderr, "turtlefft: cannot open the GPU context: %s\n", tfft_strerror(rc)); leave(1); }
         return c;
     });
 }
-[[noreturn]] void leave(int code) {
-    fflush(stdout);
-    fflush(stderr);
-    _Exit(code);
-}
+
 [[noreturn]] void die_tfft(tfft_ctx* c, int rc) {
     fprintf(stderr, "turtlefft: %s (%s)\n", tfft_strerror(rc), tfft_last_cuda_error(c));
-    exit(1);
+    leave(1);
 }
 
 void random_salt(uint8_t salt[16]) {
@@ -128,7 +133,7 @@ void random_salt(uint8_t salt[16]) {
         return;
     }
     FILE* f = fopen("/dev/urandom", "rb");  // std::random_device upstream (S:927-929)
-    if (!f || fread(salt, 1, 16, f) != 16) { fprintf(stderr, "turtlefft: no entropy source\n"); exit(1); }
+    if (!f || fread(salt, 1, 16, f) != 16) { fprintf(stderr, "turtlefft: no entropy source\n"); leave(1); }
     fclose(f);
 }
 
@@ -137,7 +142,7 @@ bool load_key(const Args& A, uint8_t master[32]) {
     if (A.key.empty()) return false;
     const int rc = tfft_host_key_decode(A.key.c_str(), A.wrap_pass.c_str(), A.iters, master);
     if (rc < 0) fprintf(stderr, "Key is wrapped but no unwrap passphrase provided\n");
-    if (rc != 1) { fprintf(stderr, "Failed to decode/unwrap key from --key argument\n"); exit(1); }  // S:936, S:1149
+    if (rc != 1) { fprintf(stderr, "Failed to decode/unwrap key from --key argument\n"); leave(1); }  // S:936, S:1149
     return true;
 }
 
@@ -146,7 +151,7 @@ void do_embed(const Args& A) {
     auto ctx_f = open_ctx_async();
     int W, H;
     uint8_t* img = tfft_host_png_load(A.in.c_str(), &W, &H);
-    if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:910
+    if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); leave(1); }  // S:910
     const int PW = next_pow2(W), PH = next_pow2(H);
     uint8_t salt[16];
     random_salt(salt);
@@ -179,11 +184,11 @@ void do_embed(const Args& A) {
                               A.center ? 1 : 0, A.magmin, A.rmin, A.rmax, out.data(), &usable, med);
     if (rc == TFFT_E_CAPACITY || wrc != 0 || (rc == TFFT_OK && nbits > usable)) {  // S:1009-1012
         fprintf(stderr, "Message too large. Need %zu bits (after ECC), capacity ~%zu bits.\n", nbits, (size_t)usable);
-        exit(1);
+        leave(1);
     }
     if (rc) die_tfft(ctx, rc);
     ph.mark("tfft_embed_batch");
-    if (!tfft_host_png_save(A.out.c_str(), out.data(), W, H)) { fprintf(stderr, "PNG write failed: %s\n", A.out.c_str()); exit(1); }  // S:1105
+    if (!tfft_host_png_save(A.out.c_str(), out.data(), W, H)) { fprintf(stderr, "PNG write failed: %s\n", A.out.c_str()); leave(1); }  // S:1105
     fprintf(stdout, "Embedded %zu bits into %s (payload %u bytes, ver=2, salt/nonce in header)\n", nbits, A.out.c_str(),
             (unsigned)A.secret.size());  // S:1107
     ph.mark("png encode");
@@ -195,7 +200,7 @@ void do_extract(const Args& A) {
     auto ctx_f = open_ctx_async();
     int W, H;
     uint8_t* img = tfft_host_png_load(A.in.c_str(), &W, &H);
-    if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); exit(1); }  // S:1115
+    if (!img) { fprintf(stderr, "Failed to load %s\n", A.in.c_str()); leave(1); }  // S:1115
     const int PW = next_pow2(W), PH = next_pow2(H);
     uint8_t path_key[32], sub[128], master[32];
     const bool raw_key = load_key(A, master);
@@ -203,7 +208,7 @@ void do_extract(const Args& A) {
     else tfft_host_turtle_keys((const uint8_t*)A.pass.data(), A.pass.size(), path_key, sub);
     std::vector<uint32_t> bins(912);
     if (tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, 912, bins.data(), nullptr, nullptr, 0)) {
-        fprintf(stderr, "Magic not found.\n"); exit(1);  // not even room for a header
+        fprintf(stderr, "Magic not found.\n"); leave(1);  // not even room for a header
     }
     ph.mark("png + keys + header walk");
     tfft_ctx* ctx = ctx_f.get();
@@ -216,16 +221,16 @@ void do_extract(const Args& A) {
     if ((rc = tfft_read_bits(ctx, bins.data(), 912, 3, jit.empty() ? nullptr : jit.data(), A.alpha, hdr, nullptr))) die_tfft(ctx, rc);
     uint32_t clen = 0;
     const int hrc = tfft_host_parse_header(hdr, &clen, nullptr, nullptr);
-    if (hrc == 1) { fprintf(stderr, "Magic not found.\n"); exit(1); }                         // S:1237
-    if (hrc == 2) { fprintf(stderr, "Unsupported version (%u).\n", hdr[4]); exit(1); }         // S:1238
+    if (hrc == 1) { fprintf(stderr, "Magic not found.\n"); leave(1); }                         // S:1237
+    if (hrc == 2) { fprintf(stderr, "Unsupported version (%u).\n", hdr[4]); leave(1); }         // S:1238
     const size_t nb = 912 + 56 * ((size_t)clen + 16);
     // a (noise- or attacker-controlled) length beyond what the annulus can hold cannot be a frame: fail like a walk that
     // ran out of bins instead of allocating for it (the reference walks forever here)
-    if (nb > (size_t)3 * PH * PW / 2) { fprintf(stderr, "Payload truncated after ECC decode.\n"); exit(1); }
+    if (nb > (size_t)3 * PH * PW / 2) { fprintf(stderr, "Payload truncated after ECC decode.\n"); leave(1); }
     bins.resize(nb);
     // the same walk continued (S:1260-1264); bounded, unlike upstream
     if (tfft_host_walk(sub, PH, PW, A.rmin, A.rmax, A.density, nb, bins.data(), nullptr, nullptr, 0)) {
-        fprintf(stderr, "Payload truncated after ECC decode.\n"); exit(1);  // S:1269
+        fprintf(stderr, "Payload truncated after ECC decode.\n"); leave(1);  // S:1269
     }
     if (A.jitter != 0.0) { jit.resize(nb); tfft_host_jitter(sub, bins.data(), nb, A.jitter, jit.data()); }
     std::vector<uint8_t> rest((size_t)clen + 16);
@@ -236,7 +241,7 @@ void do_extract(const Args& A) {
                                : tfft_host_open_payload((const uint8_t*)A.pass.data(), A.pass.size(), A.iters, hdr, rest.data(), clen);
     memset(master, 0, sizeof(master));
     if (!opened) {
-        fprintf(stderr, "Auth failed (wrong pass or data corrupted).\n"); exit(1);  // S:1308
+        fprintf(stderr, "Auth failed (wrong pass or data corrupted).\n"); leave(1);  // S:1308
     }
     std::string secret((const char*)rest.data(), clen);
     printf("%s\n", secret.c_str());  // S:1311
