@@ -145,9 +145,14 @@ int tfft_extract_frame_dev(tfft_ctx* ctx, const uint8_t* d_stego, int n, int W, 
                            uint8_t* d_out_payload, uint8_t* d_raw_bits, void* stream);
 
 /* Two-phase extract for the data dependency at S:1253 (payload length is only known after the
- * header has been decoded): tfft_forward_batch keeps the spectra of the batch resident in the
+ * header has been decoded): tfft_forward_batch keeps the transform of the batch resident in the
  * context; tfft_read_bits may then be called any number of times (header: 912 bins rep 3,
- * payload: 56*(clen+16) bins rep 7).  The batch must fit the workspace (TFFT_E_NOMEM if not). */
+ * payload: 56*(clen+16) bins rep 7).  The batch must fit the workspace (TFFT_E_NOMEM if not).
+ * What stays resident is the library's business and never changes a result: the spectra, or -- on 4096-row planes --
+ * the output of the row pass, from which the first tfft_read_bits makes either the read bits of the whole quarter plane
+ * for its alpha (no jitter, bins within stored rows 0..2047 and left of the Nyquist column; later reads with the same
+ * alpha only gather and vote) or, for any other list, the spectra.  Any other entry point called in between drops the
+ * resident state (tfft_read_bits then returns TFFT_E_STATE). */
 int tfft_forward_batch(tfft_ctx* ctx, const uint8_t* img, int n, int W, int H, int center);
 int tfft_read_bits(tfft_ctx* ctx, const uint32_t* bins, size_t nbins, int rep,
                    const double* jitter, double alpha, uint8_t* out_bytes, uint8_t* raw_bits);

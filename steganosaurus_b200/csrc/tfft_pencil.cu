@@ -1338,7 +1338,7 @@ __global__ void __launch_bounds__(Geo<LOG2N, 1>::UT* UNITS, 1) pencil_u8_fwd_r2c
             for (int i = tt; i < nch; i += G::UT) {
                 const int avail = span - i * 16;
                 const int nb = avail >= 16 ? 16 : (avail > 0 ? avail : 0);
-                cp_async16(dst + i * 16, a0 + i * 16, nb);  // nb == 0: nothing is read (pure zero fill)
+                cp_async16(dst + i * 16, nb ? a0 + i * 16 : (const unsigned char*)a.img_in, nb);  // nb == 0: nothing is read (pure zero fill; the address stays inside the batch)
             }
         }
         cp_async_commit();
