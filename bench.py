@@ -641,9 +641,32 @@ def run_ours(args):
     usable_min = int(d_usable.min().item())
     changed = float((d_stego[0] != d_cover[0]).float().mean().item())
 
-    # ---- end-to-end leg: host buffers through the C-ABI, pinned memory, copies inside the timed region
+    # ---- the plain FFT passes by themselves (the second half of BASELINE.json's metric: "FFT-pass HBM GB/s % peak"): one 1-D
+    # pass of fft2d S:359-366 over a batch of dense complex planes, in place, every element read once and written once
+    # (32 bytes per element) -- the reference's own formulation of a pass, without the half-spectrum / zero-row / window
+    # savings the embed+extract step above takes.  24 planes of PH x PW = 6.4 GB at 4096^2: far larger than L2.
     del d_cover, d_stego, d_bits
     torch.cuda.empty_cache()
+    fft_passes = None
+    if rank == 0 and max(PH, PW) <= 4096:
+        npl = 24
+        planes = torch.empty(npl, PH, PW, 2, dtype=torch.float64, device=dev).normal_()
+        fft_passes = {"planes": npl, "PH": PH, "PW": PW, "bytes_per_pass": 32 * npl * PH * PW, "unit": "GB/s"}
+        for nm, axis, inv in (("row_fwd", 0, False), ("col_fwd", 1, False), ("col_inv", 1, True), ("row_inv", 0, True)):
+            for _ in range(2):
+                ctx.fft_pass_dev(planes, axis, inv)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(3):
+                ctx.fft_pass_dev(planes, axis, inv)
+            p1.record()
+            torch.cuda.synchronize()
+            gbs = 32 * npl * PH * PW / 1e9 / (p0.elapsed_time(p1) / 3 / 1e3)
+            fft_passes[nm] = round(gbs, 1)
+        del planes
+        torch.cuda.empty_cache()
+
+    # ---- end-to-end leg: host buffers through the C-ABI, pinned memory, copies inside the timed region
     h_cover = torch.from_numpy(covers_np).pin_memory()
     # frame bits cross the link packed eight to a byte, MSB first (tfft_embed_batch_packed; the order of S:447-459)
     h_bits = torch.from_numpy(np.packbits(bits_np, axis=1)).pin_memory()
@@ -743,6 +766,9 @@ def run_ours(args):
                      "kernels": kernels},
         "cpu_baseline": cpu_base,
     }
+    if fft_passes:
+        fft_passes["frac_of_peak"] = {k: round(v / peak, 3) for k, v in fft_passes.items() if k.endswith(("_fwd", "_inv"))} if peak else None
+        line["fft_passes"] = fft_passes
     print(json.dumps(line), flush=True)
     return 0
 

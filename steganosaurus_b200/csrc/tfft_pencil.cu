@@ -14,16 +14,21 @@
 //
 // Kernels:
 //   pencil_u8_fwd_r2c / pencil_u8_inv_c2r   fused u8 RGB <-> half-spectrum rows; two image rows share one complex
-//                                           transform, or (WIDE) one 8192-pixel row is packed into one
+//                                           transform, or (WIDE) one 8192-pixel row is packed into one; FOLD (forward,
+//                                           8192-row planes of an extract): rows y and y + 4096 leave as the two inputs
+//                                           of two 4096-point column transforms (first radix-2 step of the column pass)
+//   pencil_col_embed_w                      column-resident embed: forward columns, |F|^2 for the median, phase write on
+//                                           the registers that own the bins, inverse columns -- one residency per pair
 //   pencil_col_tma_w                        4096-point column pairs on the TMA engine, mbarrier hand-offs, zero-block skipping;
-//                                           embed forward: also the median sample and a float copy of |F|^2; extract
-//                                           forward (SIGN): no spectrum, one read bit per element
+//                                           unfused embed forward: also the median sample and a float copy of |F|^2;
+//                                           extract forward (SIGN): no spectrum, one read bit per element
 //   pencil_col_tma, pencil_c2c, pencil_u8_fwd/inv   other sizes / full-spectrum variants / LSU fallback
 //
 // A "unit" is the set of threads that owns one buffer set and works through its own stream of pencils (persistent,
 // static round-robin); row CTAs host two units that only synchronise among themselves (named barriers).
-// What bounds them (profiles/r1b_experiments.txt): columns = TMA/L2 request path for 32-byte-inner boxes, rows =
-// shared-memory/LSU pipe; the FP64 butterflies are (almost) hidden under the data movement.
+// What bounds them (profiles/r2_experiments.txt): the FP64 pipe (~730 instructions per thread and
+// transform) and the shared-memory pipe (~100 16-byte accesses) carry about the same load and take turns, because the
+// warps of a CTA sit in the same phase; HBM is 35 % busy.  What pays is taking work off either pipe.
 // Reference citations S:n = steganosaurus/src/steganosaur.cpp line n.
 #include "tfft_kernels.cuh"
 
