@@ -650,20 +650,23 @@ def run_ours(args):
     fft_passes = None
     if rank == 0 and max(PH, PW) <= 4096:
         npl = 24
-        planes = torch.empty(npl, PH, PW, 2, dtype=torch.float64, device=dev).normal_()
         fft_passes = {"planes": npl, "PH": PH, "PW": PW, "bytes_per_pass": 32 * npl * PH * PW, "unit": "GB/s"}
-        for nm, axis, inv in (("row_fwd", 0, False), ("col_fwd", 1, False), ("col_inv", 1, True), ("row_inv", 0, True)):
-            for _ in range(2):
-                ctx.fft_pass_dev(planes, axis, inv)
-            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            p0.record()
-            for _ in range(3):
-                ctx.fft_pass_dev(planes, axis, inv)
-            p1.record()
-            torch.cuda.synchronize()
-            gbs = 32 * npl * PH * PW / 1e9 / (p0.elapsed_time(p1) / 3 / 1e3)
-            fft_passes[nm] = round(gbs, 1)
-        del planes
+        try:  # (an extra: whatever happens here must not cost the line its headline numbers)
+            planes = torch.view_as_complex(torch.empty(npl, PH, PW, 2, dtype=torch.float64, device=dev).normal_())
+            for nm, axis, inv in (("row_fwd", 0, False), ("col_fwd", 1, False), ("col_inv", 1, True), ("row_inv", 0, True)):
+                for _ in range(2):
+                    ctx.fft_pass_dev(planes, axis, inv)
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for _ in range(3):
+                    ctx.fft_pass_dev(planes, axis, inv)
+                p1.record()
+                torch.cuda.synchronize()
+                gbs = 32 * npl * PH * PW / 1e9 / (p0.elapsed_time(p1) / 3 / 1e3)
+                fft_passes[nm] = round(gbs, 1)
+            del planes
+        except Exception as e:  # noqa: BLE001
+            fft_passes["error"] = repr(e)[:200]
         torch.cuda.empty_cache()
 
     # ---- end-to-end leg: host buffers through the C-ABI, pinned memory, copies inside the timed region
